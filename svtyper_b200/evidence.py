@@ -144,6 +144,8 @@ class LibraryTable(object):
     def __init__(self, libs):
         """libs: iterable of (mean, sd, {insert_size: count})."""
         f64, i32, chunks, off = [], [], [], 0
+        libs = list(libs)
+        self.sources = libs              # kept for host-side consumers (fetch flank, tests)
         for mean, sd, hist in libs:
             mean, sd = float(mean), float(sd)
             flank = mean + sd * 3
