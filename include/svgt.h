@@ -1,0 +1,126 @@
+/*
+ * svgt.h -- C ABI of the B200-native SV genotype-likelihood engine (libsvgt.so).
+ *
+ * This is the drop-in boundary for ONE path of hall-lab/svtyper v0.7.1: the scoring
+ * segment of a breakpoint batch,
+ *
+ *     counts = tally_variant_read_fragments(split_slop, min_aligned, breakpoint,
+ *                                           sam_fragments, debug)   singlesample.py:355
+ *     result = bayesian_genotype(breakpoint, counts, split_weight,
+ *                                disc_weight, debug)                singlesample.py:406
+ *
+ * as called per breakpoint inside parallel_calculate_genotype (singlesample.py:523-536),
+ * serial_calculate_genotype (:486-498) and, inlined, classic.sv_genotype
+ * (classic.py:286-495).  One call scores a whole batch of breakpoints.  Read gathering
+ * (pysam) and VCF I/O stay on the host side of this boundary.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  All entry points return 0 on
+ * success or a negative svgt_err code, never throw, and are re-entrant per stream.
+ * Row layouts are documented in svtyper_b200/evidence.py and DESIGN.md.
+ */
+#ifndef SVGT_H
+#define SVGT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGT_ABI_VERSION 1
+
+#define SVGT_SITE_WORDS 16  /* int32 words per site row      (64 B) */
+#define SVGT_FRAG_WORDS 8   /* int32 words per fragment row  (32 B) */
+#define SVGT_SPLIT_WORDS 8  /* int32 words per split row     (32 B) */
+#define SVGT_OUT_BYTES 80   /* f64 GL[3], f64 SQ, int32 GT,GQ,DP,RO,AO,QR,QA,RS,AS,ASC,RP,AP */
+
+enum svgt_err {
+    SVGT_OK = 0,
+    SVGT_ERR_ARG = -1,          /* null pointer / negative size / bad mode            */
+    SVGT_ERR_CUDA = -2,         /* CUDA runtime error, see svgt_last_error()          */
+    SVGT_ERR_LOG_TABLE = -3,    /* a site's QR+QA exceeded the log10 table (n_log)    */
+    SVGT_ERR_LIB_INDEX = -4,    /* a fragment row names a library >= n_lib            */
+    SVGT_ERR_NO_DEVICE = -5,    /* no CUDA device (there is no CPU fallback)          */
+    SVGT_ERR_RANGE = -6         /* a site coordinate / window is outside +-2^30       */
+};
+
+/* assoc_mode: which reference entry point's floating-point association order to follow */
+#define SVGT_ASSOC_SSO 0      /* singlesample.py:367-378: per-fragment sub-totals      */
+#define SVGT_ASSOC_CLASSIC 1  /* classic.py:311,326-328: every read added straight in  */
+
+/* Output GT codes (reference singlesample.py:462-471, :207-243) */
+#define SVGT_GT_UNDERFLOW (-1) /* "./." with GL/counts kept: all 10**GL underflowed   */
+#define SVGT_GT_BLANK (-2)     /* no evidence: the blank_genotype_result() row        */
+#define SVGT_GT_SKIPPED (-3)   /* site row had the SKIP bit (too many reads)          */
+
+typedef struct svgt_out_row {
+    double gl[3];
+    double sq;
+    int32_t gt, gq, dp, ro, ao, qr, qa, rs, as_, asc, rp, ap;
+} svgt_out_row_t;
+
+/*
+ * One batch.  In svgt_score_batch() every pointer is a DEVICE pointer; in
+ * svgt_ctx_score_host() every pointer is a HOST pointer.
+ */
+typedef struct svgt_batch {
+    const int32_t *sites;   int64_t n_sites;  /* [n_sites][16]                           */
+    const int32_t *frags;   int64_t n_frag;   /* [n_frag][8]  sorted(query_name) per site */
+    const int32_t *splits;  int64_t n_split;  /* [n_split][8]                            */
+    const int32_t *order;                     /* optional site permutation (work-bucketed
+                                                 launch order), NULL = identity          */
+    const double *lib_f64;                    /* [n_lib][4] flank, 2*sd, N, mean         */
+    const int32_t *lib_i32;                   /* [n_lib][4] hist_off, hist_len, nondel_L */
+    int32_t n_lib;
+    const uint32_t *hist;   int64_t n_hist;   /* insert-size histogram counts            */
+    const double *pm;                         /* [256]   prob_mapq LUT (utils.py:74)     */
+    const double *logt;     int64_t n_log;    /* [n_log] math.log(n, 10) LUT             */
+    const double *consts;                     /* [32]    priors / log10 prior constants  */
+    int32_t min_aligned;                      /* reference -m, default 20                */
+    int32_t split_slop;                       /* reference constant 3                    */
+    int32_t assoc_mode;                       /* SVGT_ASSOC_*                            */
+    int32_t reserved;
+    double split_weight, disc_weight;         /* reference --split_weight/--disc_weight  */
+} svgt_batch_t;
+
+int svgt_abi_version(void);
+const char *svgt_last_error(void);            /* thread-local, valid until the next call */
+int svgt_device_count(void);
+
+/*
+ * Score a device-resident batch.  Asynchronous on `stream` (a cudaStream_t passed as
+ * void*).  `out_rows` = n_sites * 80 device bytes in ORIGINAL site order.  `status` = 4
+ * device int32 words, zeroed by the call; after the stream is synchronised status[0] is
+ * 0 or the first svgt_err a site raised.  The callee allocates nothing.
+ */
+int svgt_score_batch(const svgt_batch_t *batch, void *out_rows, int32_t *status, void *stream);
+
+/* Number of kernel launches svgt_score_batch issues for this batch (bench bookkeeping). */
+int svgt_launches_per_batch(const svgt_batch_t *batch);
+
+/*
+ * Row-delivery variant of the scoring kernel (same results, different memory path):
+ * 0 = per-lane 128-bit global loads with register prefetch, 1 = per-lane cp.async.bulk
+ * (TMA 1-D) ring in shared memory.  -1 restores the built-in default (or the
+ * SVGT_VARIANT environment variable).  Returns the variant now in force.
+ */
+int svgt_set_variant(int variant);
+
+/*
+ * Host-buffer convenience used by the reference-facing plug-in: owns device staging
+ * buffers and a stream on `device`, copies the batch host->device, scores it, copies
+ * the 80-byte rows back into `out_rows_host`, and synchronises.  Returns 0 or svgt_err.
+ */
+typedef struct svgt_ctx svgt_ctx_t;
+int svgt_ctx_create(int device, svgt_ctx_t **ctx);
+int svgt_ctx_destroy(svgt_ctx_t *ctx);
+int svgt_ctx_score_host(svgt_ctx_t *ctx, const svgt_batch_t *host_batch, void *out_rows_host);
+/* bytes moved by the last svgt_ctx_score_host call */
+int svgt_ctx_last_traffic(const svgt_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* device time (ms, CUDA events) of the kernel(s) in the last svgt_ctx_score_host call */
+int svgt_ctx_last_kernel_ms(const svgt_ctx_t *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGT_H */

@@ -1,0 +1,267 @@
+/*
+ * svgt_api.cu -- the C ABI of libsvgt.so (declared in include/svgt.h).
+ *
+ * svgt_score_batch() replaces, for a whole batch of breakpoints, the per-breakpoint
+ * calls tally_variant_read_fragments + bayesian_genotype of the reference
+ * (svtyper/singlesample.py:523-536, :486-498; inlined in svtyper/classic.py:286-495).
+ * There is no CPU fallback: without a CUDA device every compute entry point returns
+ * SVGT_ERR_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "svgt_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_variant = -1;   /* -1: default / environment */
+
+int fail(int code, const char *fmt, const char *detail)
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return SVGT_ERR_CUDA;
+}
+
+int current_variant()
+{
+    if (g_variant >= 0) return g_variant;
+    const char *env = getenv("SVGT_VARIANT");
+    if (env && *env) {
+        int v = atoi(env);
+        if (v >= 0 && v < SVGT_VAR_COUNT) return v;
+    }
+    return SVGT_VAR_DIRECT;
+}
+
+int check_batch(const svgt_batch_t *b)
+{
+    if (!b) return fail(SVGT_ERR_ARG, "null batch%s", nullptr);
+    if (b->n_sites < 0 || b->n_frag < 0 || b->n_split < 0 || b->n_lib < 0 || b->n_hist < 0 || b->n_log < 2)
+        return fail(SVGT_ERR_ARG, "negative size in batch%s", nullptr);
+    if (b->n_sites > 0 && !b->sites) return fail(SVGT_ERR_ARG, "null %s", "sites");
+    if (b->n_frag > 0 && !b->frags) return fail(SVGT_ERR_ARG, "null %s", "frags");
+    if (b->n_split > 0 && !b->splits) return fail(SVGT_ERR_ARG, "null %s", "splits");
+    if (b->n_lib > 0 && (!b->lib_f64 || !b->lib_i32 || !b->hist)) return fail(SVGT_ERR_ARG, "null %s", "library tables");
+    if (!b->pm || !b->logt || !b->consts) return fail(SVGT_ERR_ARG, "null %s", "look-up tables");
+    if (b->assoc_mode != SVGT_ASSOC_SSO && b->assoc_mode != SVGT_ASSOC_CLASSIC)
+        return fail(SVGT_ERR_ARG, "bad %s", "assoc_mode");
+    if (b->n_sites / 32 >= 0x7fffffffLL) return fail(SVGT_ERR_ARG, "too many %s", "sites");
+    const uintptr_t align = (uintptr_t)b->sites | (uintptr_t)b->frags | (uintptr_t)b->splits | (uintptr_t)b->lib_i32;
+    if (align & 15) return fail(SVGT_ERR_ARG, "%s must be 16-byte aligned", "row arrays");
+    return SVGT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svgt_abi_version(void) { return SVGT_ABI_VERSION; }
+
+const char *svgt_last_error(void) { return g_err; }
+
+int svgt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int svgt_set_variant(int variant)
+{
+    if (variant >= SVGT_VAR_COUNT) return fail(SVGT_ERR_ARG, "bad %s", "variant");
+    g_variant = variant < 0 ? -1 : variant;
+    return current_variant();
+}
+
+int svgt_launches_per_batch(const svgt_batch_t *batch)
+{
+    if (!batch) return fail(SVGT_ERR_ARG, "null batch%s", nullptr);
+    return batch->n_sites > 0 ? 1 : 0;
+}
+
+int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, void *stream)
+{
+    int rc = check_batch(b);
+    if (rc != SVGT_OK) return rc;
+    if (!status || (b->n_sites > 0 && !out_rows)) return fail(SVGT_ERR_ARG, "null %s", "out_rows/status");
+    if ((uintptr_t)out_rows & 15) return fail(SVGT_ERR_ARG, "%s must be 16-byte aligned", "out_rows");
+    if (svgt_device_count() <= 0) return fail(SVGT_ERR_NO_DEVICE, "no CUDA device%s", nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(status)");
+    if (b->n_sites == 0) return SVGT_OK;
+
+    SvgtParams p;
+    memset(&p, 0, sizeof(p));
+    p.sites = (const int4 *)b->sites; p.n_sites = b->n_sites;
+    p.frags = (const int4 *)b->frags; p.n_frag = b->n_frag;
+    p.splits = (const int4 *)b->splits; p.n_split = b->n_split;
+    p.order = b->order;
+    p.lib_f64 = b->lib_f64; p.lib_i32 = (const int4 *)b->lib_i32; p.n_lib = b->n_lib;
+    p.hist = b->hist; p.n_hist = b->n_hist;
+    p.pm = b->pm; p.logt = b->logt; p.n_log = b->n_log; p.consts = b->consts;
+    p.min_aligned = b->min_aligned; p.split_slop = b->split_slop; p.assoc_mode = b->assoc_mode;
+    p.split_weight = b->split_weight; p.disc_weight = b->disc_weight;
+    p.out = (svgt_out_row_t *)out_rows;
+    p.status = status;
+    p.n_tiles = (int)((b->n_sites + 31) / 32);
+    p.hist_in_smem = (b->n_hist <= SVGT_SMEM_HIST_WORDS) ? 1 : 0;
+    e = (cudaError_t)svgt_launch_score(p, current_variant(), st);
+    if (e != cudaSuccess) return cuda_fail(e, "svgt_score_kernel launch");
+    return SVGT_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* host-buffer context                                                                   */
+/* ------------------------------------------------------------------------------------ */
+struct svgt_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    void *buf[12];
+    size_t cap[12];
+    int64_t h2d, d2h;
+    float kernel_ms;
+};
+
+enum { B_SITES, B_FRAGS, B_SPLITS, B_ORDER, B_LIBF, B_LIBI, B_HIST, B_PM, B_LOG, B_CONSTS, B_OUT, B_STATUS };
+
+static int ctx_reserve(svgt_ctx *c, int slot, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (c->cap[slot] >= bytes) return SVGT_OK;
+    if (c->buf[slot]) cudaFree(c->buf[slot]);
+    c->buf[slot] = nullptr; c->cap[slot] = 0;
+    size_t want = bytes + bytes / 8;           /* a little slack so steady-state batches never regrow */
+    cudaError_t e = cudaMalloc(&c->buf[slot], want);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    c->cap[slot] = want;
+    return SVGT_OK;
+}
+
+static int ctx_upload(svgt_ctx *c, int slot, const void *src, size_t bytes)
+{
+    int rc = ctx_reserve(c, slot, bytes);
+    if (rc != SVGT_OK) return rc;
+    if (bytes == 0) return SVGT_OK;
+    cudaError_t e = cudaMemcpyAsync(c->buf[slot], src, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    c->h2d += (int64_t)bytes;
+    return SVGT_OK;
+}
+
+int svgt_ctx_create(int device, svgt_ctx_t **out)
+{
+    if (!out) return fail(SVGT_ERR_ARG, "null %s", "ctx pointer");
+    *out = nullptr;
+    int n = svgt_device_count();
+    if (n <= 0) return fail(SVGT_ERR_NO_DEVICE, "no CUDA device%s", nullptr);
+    if (device < 0 || device >= n) return fail(SVGT_ERR_ARG, "bad %s", "device index");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    svgt_ctx *c = (svgt_ctx *)calloc(1, sizeof(svgt_ctx));
+    if (!c) return fail(SVGT_ERR_ARG, "out of %s", "host memory");
+    c->device = device;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { free(c); return cuda_fail(e, "cudaStreamCreate"); }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return SVGT_OK;
+}
+
+int svgt_ctx_destroy(svgt_ctx_t *c)
+{
+    if (!c) return SVGT_OK;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 12; ++i)
+        if (c->buf[i]) cudaFree(c->buf[i]);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    free(c);
+    return SVGT_OK;
+}
+
+int svgt_ctx_score_host(svgt_ctx_t *c, const svgt_batch_t *hb, void *out_rows_host)
+{
+    if (!c) return fail(SVGT_ERR_ARG, "null %s", "ctx");
+    int rc = check_batch(hb);
+    if (rc != SVGT_OK) return rc;
+    if (hb->n_sites > 0 && !out_rows_host) return fail(SVGT_ERR_ARG, "null %s", "out_rows_host");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    c->h2d = c->d2h = 0;
+    c->kernel_ms = 0.f;
+
+    svgt_batch_t db = *hb;
+#define UP(slot, field, type, count)                                                          \
+    do {                                                                                      \
+        rc = ctx_upload(c, slot, hb->field, (size_t)(count) * sizeof(type));                  \
+        if (rc != SVGT_OK) return rc;                                                         \
+        db.field = (const type *)c->buf[slot];                                                \
+    } while (0)
+    UP(B_SITES, sites, int32_t, hb->n_sites * SVGT_SITE_WORDS);
+    UP(B_FRAGS, frags, int32_t, hb->n_frag * SVGT_FRAG_WORDS);
+    UP(B_SPLITS, splits, int32_t, hb->n_split * SVGT_SPLIT_WORDS);
+    if (hb->order) UP(B_ORDER, order, int32_t, hb->n_sites);
+    UP(B_LIBF, lib_f64, double, hb->n_lib * 4);
+    UP(B_LIBI, lib_i32, int32_t, hb->n_lib * 4);
+    UP(B_HIST, hist, uint32_t, hb->n_hist);
+    UP(B_PM, pm, double, 256);
+    UP(B_LOG, logt, double, hb->n_log);
+    UP(B_CONSTS, consts, double, 32);
+#undef UP
+    if ((rc = ctx_reserve(c, B_OUT, (size_t)hb->n_sites * SVGT_OUT_BYTES)) != SVGT_OK) return rc;
+    if ((rc = ctx_reserve(c, B_STATUS, 16)) != SVGT_OK) return rc;
+
+    cudaEventRecord(c->ev0, c->stream);
+    rc = svgt_score_batch(&db, c->buf[B_OUT], (int32_t *)c->buf[B_STATUS], c->stream);
+    if (rc != SVGT_OK) return rc;
+    cudaEventRecord(c->ev1, c->stream);
+
+    int32_t status[4] = {0, 0, 0, 0};
+    if (hb->n_sites > 0) {
+        e = cudaMemcpyAsync(out_rows_host, c->buf[B_OUT], (size_t)hb->n_sites * SVGT_OUT_BYTES,
+                            cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H)");
+        c->d2h += hb->n_sites * (int64_t)SVGT_OUT_BYTES;
+    }
+    e = cudaMemcpyAsync(status, c->buf[B_STATUS], sizeof(status), cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(status)");
+    c->d2h += (int64_t)sizeof(status);
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    cudaEventElapsedTime(&c->kernel_ms, c->ev0, c->ev1);
+    if (status[0] != 0) {
+        char msg[64];
+        snprintf(msg, sizeof(msg), "%d site(s), first code %d", status[2], status[0]);
+        return fail(status[0], "scoring kernel flagged %s", msg);
+    }
+    return SVGT_OK;
+}
+
+int svgt_ctx_last_traffic(const svgt_ctx_t *c, int64_t *h2d_bytes, int64_t *d2h_bytes)
+{
+    if (!c) return fail(SVGT_ERR_ARG, "null %s", "ctx");
+    if (h2d_bytes) *h2d_bytes = c->h2d;
+    if (d2h_bytes) *d2h_bytes = c->d2h;
+    return SVGT_OK;
+}
+
+int svgt_ctx_last_kernel_ms(const svgt_ctx_t *c, float *ms)
+{
+    if (!c || !ms) return fail(SVGT_ERR_ARG, "null %s", "ctx/ms");
+    *ms = c->kernel_ms;
+    return SVGT_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,174 @@
+"""Host-side driver of the scoring kernels: EvidenceBatch -> device -> OUT_DTYPE rows.
+
+PyTorch is used for what it is good at here -- device memory, streams, pinned host
+buffers, torch.distributed -- and nothing else: every byte of arithmetic happens in
+libsvgt.so (svtyper_b200/csrc), reached through the C ABI of include/svgt.h.
+
+Two call shapes, both replacing the reference's per-breakpoint
+`tally_variant_read_fragments` + `bayesian_genotype` pair
+(reference svtyper/singlesample.py:523-536) for a whole batch:
+
+  Engine.score_host(batch)      host numpy arrays in, OUT_DTYPE numpy rows out
+                                (svgt_ctx_score_host: H2D, kernel, D2H)
+  Engine.upload(batch) + Engine.score(dev)   device-resident, asynchronous
+                                (svgt_score_batch)
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import evidence as ev
+from . import native
+
+_LUT_CACHE = {}
+
+
+def luts_for(n_log):
+    """Host LUTs (CPython math), cached by rounded-up table size."""
+    size = 1 << max(10, int(n_log - 1).bit_length())
+    if size not in _LUT_CACHE:
+        _LUT_CACHE[size] = ev.build_luts(size)
+    return _LUT_CACHE[size]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceBatch(object):
+    """An EvidenceBatch resident in HBM plus its svgt_batch_t descriptor."""
+
+    def __init__(self, tensors, desc, n_sites, algorithmic_bytes):
+        self.tensors = tensors          # keeps the device memory alive
+        self.desc = desc                # native.SvgtBatch with device pointers
+        self.n_sites = n_sites
+        self.algorithmic_bytes = algorithmic_bytes
+        self.out = None
+        self.status = None
+
+
+def _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode):
+    d = native.SvgtBatch()
+    d.sites, d.n_sites = ptr["sites"], batch.n_sites
+    d.frags, d.n_frag = ptr["frags"], batch.n_frag
+    d.splits, d.n_split = ptr["splits"], batch.n_split
+    d.order = ptr.get("order")
+    d.lib_f64, d.lib_i32, d.n_lib = ptr["lib_f64"], ptr["lib_i32"], batch.libs.n_lib
+    d.hist, d.n_hist = ptr["hist"], int(batch.libs.hist.size)
+    d.pm, d.logt, d.n_log, d.consts = ptr["pm"], ptr["logt"], int(n_log), ptr["consts"]
+    d.min_aligned, d.split_slop, d.assoc_mode = int(min_aligned), int(split_slop), int(assoc_mode)
+    d.split_weight, d.disc_weight = float(split_weight), float(disc_weight)
+    return d
+
+
+def host_arrays(batch, split_weight=1.0, disc_weight=1.0):
+    """name -> contiguous numpy array for every field of svgt_batch_t."""
+    pm, logt, consts = luts_for(batch.log_table_size(split_weight, disc_weight))
+    arrs = {
+        "sites": batch.sites, "frags": batch.frags, "splits": batch.splits,
+        "lib_f64": batch.libs.lib_f64, "lib_i32": batch.libs.lib_i32, "hist": batch.libs.hist,
+        "pm": pm, "logt": logt, "consts": consts,
+    }
+    if batch.order is not None:
+        arrs["order"] = batch.order
+    return {k: np.ascontiguousarray(v) for k, v in arrs.items()}
+
+
+class Engine(object):
+    """One scoring engine per process / GPU."""
+
+    def __init__(self, device=None):
+        torch = _torch()
+        self._lib = native.lib()            # raises if libsvgt.so is missing
+        if not torch.cuda.is_available() or self._lib.svgt_device_count() <= 0:
+            raise native.SvgtError(native.ERR_NO_DEVICE, "no CUDA device; svtyper_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self._ctx = ctypes.c_void_p()
+        native.check(self._lib.svgt_ctx_create(self.device.index, ctypes.byref(self._ctx)))
+        self.last_h2d = self.last_d2h = 0
+        self.last_kernel_ms = 0.0
+        self.launches = 0                   # kernels launched through this engine
+
+    def close(self):
+        if self._ctx:
+            self._lib.svgt_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- host buffers in/out
+    def score_host(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
+                   assoc_mode=ev.ASSOC_SSO, arrays=None, out=None):
+        """Score a host EvidenceBatch; returns OUT_DTYPE rows (numpy).
+
+        `arrays` may carry pre-built (e.g. pinned) host arrays from `host_arrays()`;
+        `out` a pre-allocated (e.g. pinned) uint8/OUT_DTYPE buffer of n_sites rows.
+        """
+        arrs = arrays if arrays is not None else host_arrays(batch, split_weight, disc_weight)
+        ptr = {k: (v.data_ptr() if hasattr(v, "data_ptr") else v.ctypes.data) for k, v in arrs.items()}
+        n_log = arrs["logt"].numel() if hasattr(arrs["logt"], "numel") else arrs["logt"].size
+        desc = _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode)
+        if out is None:
+            out = np.zeros(batch.n_sites, dtype=ev.OUT_DTYPE)
+        optr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        rc = self._lib.svgt_ctx_score_host(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
+        h2d, d2h, ms = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_float()
+        self._lib.svgt_ctx_last_traffic(self._ctx, ctypes.byref(h2d), ctypes.byref(d2h))
+        self._lib.svgt_ctx_last_kernel_ms(self._ctx, ctypes.byref(ms))
+        self.last_h2d, self.last_d2h, self.last_kernel_ms = h2d.value, d2h.value, ms.value
+        self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(desc))
+        native.check(rc)
+        return out
+
+    # ---------------------------------------------------------------- device resident
+    def upload(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
+               assoc_mode=ev.ASSOC_SSO):
+        torch = _torch()
+        arrs = host_arrays(batch, split_weight, disc_weight)
+        tens = {}
+        for k, a in arrs.items():
+            if a.dtype == np.uint32:
+                a = a.view(np.int32)
+            t = torch.from_numpy(a) if a.size else torch.zeros(4, dtype=torch.from_numpy(a).dtype)
+            tens[k] = t.to(self.device)
+        ptr = {k: t.data_ptr() for k, t in tens.items()}
+        desc = _descriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
+                           disc_weight, assoc_mode)
+        dev = DeviceBatch(tens, desc, batch.n_sites, batch.algorithmic_bytes())
+        dev.out = torch.zeros((max(batch.n_sites, 1), ev.OUT_BYTES), dtype=torch.uint8, device=self.device)
+        dev.status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        return dev
+
+    def score(self, dev, stream=None):
+        """Asynchronously score a DeviceBatch on `stream` (default: torch's current stream).
+
+        Returns dev.out (uint8 [n_sites, 80] device tensor).  Call `check(dev)` after a
+        synchronisation to surface per-site error flags.
+        """
+        torch = _torch()
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        with torch.cuda.device(self.device):
+            rc = self._lib.svgt_score_batch(ctypes.byref(dev.desc), ctypes.c_void_p(dev.out.data_ptr()),
+                                            ctypes.c_void_p(dev.status.data_ptr()),
+                                            ctypes.c_void_p(s.cuda_stream))
+        native.check(rc)
+        self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(dev.desc))
+        return dev.out
+
+    def check(self, dev):
+        st = dev.status.cpu().numpy()
+        if st[0] != 0:
+            raise native.SvgtError(int(st[0]), "scoring kernel flagged %d thread(s)" % int(st[2]))
+
+    def rows(self, dev):
+        """Device results -> OUT_DTYPE numpy rows (synchronises)."""
+        self.check(dev)
+        raw = dev.out[:dev.n_sites].cpu().numpy()
+        return raw.reshape(-1).view(ev.OUT_DTYPE).copy()

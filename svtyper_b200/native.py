@@ -1,0 +1,99 @@
+"""ctypes binding of libsvgt.so (the C ABI declared in include/svgt.h).
+
+The library is built in-tree by `svtyper_b200.build.build_native()` (nvcc, sm_100a).
+There is no CPU fallback: if the library is missing, or no CUDA device is visible, the
+compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsvgt.so")
+
+ABI_VERSION = 1
+OK, ERR_ARG, ERR_CUDA, ERR_LOG_TABLE, ERR_LIB_INDEX, ERR_NO_DEVICE, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6
+ERR_NAMES = {ERR_ARG: "SVGT_ERR_ARG", ERR_CUDA: "SVGT_ERR_CUDA", ERR_LOG_TABLE: "SVGT_ERR_LOG_TABLE",
+             ERR_LIB_INDEX: "SVGT_ERR_LIB_INDEX", ERR_NO_DEVICE: "SVGT_ERR_NO_DEVICE",
+             ERR_RANGE: "SVGT_ERR_RANGE"}
+VAR_DIRECT, VAR_BULK = 0, 1
+
+# every symbol include/svgt.h declares (tests check the library exports all of them)
+SYMBOLS = ("svgt_abi_version", "svgt_last_error", "svgt_device_count", "svgt_score_batch",
+           "svgt_launches_per_batch", "svgt_set_variant", "svgt_ctx_create", "svgt_ctx_destroy",
+           "svgt_ctx_score_host", "svgt_ctx_last_traffic", "svgt_ctx_last_kernel_ms")
+
+
+class SvgtBatch(ctypes.Structure):
+    """struct svgt_batch (include/svgt.h)."""
+    _fields_ = [
+        ("sites", ctypes.c_void_p), ("n_sites", ctypes.c_int64),
+        ("frags", ctypes.c_void_p), ("n_frag", ctypes.c_int64),
+        ("splits", ctypes.c_void_p), ("n_split", ctypes.c_int64),
+        ("order", ctypes.c_void_p),
+        ("lib_f64", ctypes.c_void_p), ("lib_i32", ctypes.c_void_p), ("n_lib", ctypes.c_int32),
+        ("hist", ctypes.c_void_p), ("n_hist", ctypes.c_int64),
+        ("pm", ctypes.c_void_p),
+        ("logt", ctypes.c_void_p), ("n_log", ctypes.c_int64),
+        ("consts", ctypes.c_void_p),
+        ("min_aligned", ctypes.c_int32), ("split_slop", ctypes.c_int32),
+        ("assoc_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("split_weight", ctypes.c_double), ("disc_weight", ctypes.c_double),
+    ]
+
+
+class SvgtError(RuntimeError):
+    def __init__(self, code, message):
+        self.code = code
+        RuntimeError.__init__(self, "%s (%d): %s" % (ERR_NAMES.get(code, "SVGT_ERR"), code, message))
+
+
+_lib = None
+
+
+def lib():
+    """Load libsvgt.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libsvgt.so is not built: run `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` (needs nvcc); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.svgt_abi_version.restype = ctypes.c_int
+        L.svgt_last_error.restype = ctypes.c_char_p
+        L.svgt_device_count.restype = ctypes.c_int
+        L.svgt_set_variant.restype = ctypes.c_int
+        L.svgt_set_variant.argtypes = [ctypes.c_int]
+        L.svgt_launches_per_batch.restype = ctypes.c_int
+        L.svgt_launches_per_batch.argtypes = [ctypes.POINTER(SvgtBatch)]
+        L.svgt_score_batch.restype = ctypes.c_int
+        L.svgt_score_batch.argtypes = [ctypes.POINTER(SvgtBatch), ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]
+        L.svgt_ctx_create.restype = ctypes.c_int
+        L.svgt_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.svgt_ctx_destroy.restype = ctypes.c_int
+        L.svgt_ctx_destroy.argtypes = [ctypes.c_void_p]
+        L.svgt_ctx_score_host.restype = ctypes.c_int
+        L.svgt_ctx_score_host.argtypes = [ctypes.c_void_p, ctypes.POINTER(SvgtBatch), ctypes.c_void_p]
+        L.svgt_ctx_last_traffic.restype = ctypes.c_int
+        L.svgt_ctx_last_traffic.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                                            ctypes.POINTER(ctypes.c_int64)]
+        L.svgt_ctx_last_kernel_ms.restype = ctypes.c_int
+        L.svgt_ctx_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        if L.svgt_abi_version() != ABI_VERSION:
+            raise ImportError("libsvgt.so ABI %d != expected %d" % (L.svgt_abi_version(), ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise SvgtError(rc, lib().svgt_last_error().decode("utf-8", "replace"))
+
+
+def set_variant(v):
+    rc = lib().svgt_set_variant(int(v))
+    if rc < 0:
+        check(rc)
+    return rc

@@ -75,12 +75,12 @@ def _mapq_sampler(rng, n):
     return q
 
 
-def generate(config="del10k", n_sites=None, seed=None, rank=0, bucket=True) -> ev.EvidenceBatch:
+def generate(config="del10k", n_sites=None, seed=None, rank=0, bucket=True, libs=None) -> ev.EvidenceBatch:
     cfg = CONFIGS[config]
     n = int(cfg["n_sites"] if n_sites is None else n_sites)
     seed = (BASE_SEED + cfg["seed_off"]) if seed is None else seed
     rng = np.random.Generator(np.random.Philox(key=[seed, rank]))
-    libs = make_libraries(cfg["n_lib"])
+    libs = make_libraries(cfg["n_lib"]) if libs is None else libs
     n_lib = libs.n_lib
     flank = libs.lib_f64[:, 0]
 
@@ -126,7 +126,8 @@ def generate(config="del10k", n_sites=None, seed=None, rank=0, bucket=True) -> e
     site_of = np.repeat(np.arange(n), nfrag)
 
     # ---------------- fragments ----------------
-    lib = rng.choice(n_lib, size=N, p=np.array([0.4, 0.3, 0.2, 0.1][:n_lib]) / sum([0.4, 0.3, 0.2, 0.1][:n_lib]))
+    lib_p = np.array(([0.4, 0.3, 0.2, 0.1] + [0.05] * n_lib)[:n_lib])
+    lib = rng.choice(n_lib, size=N, p=lib_p / lib_p.sum())
     # insert size ~ library histogram (inverse CDF)
     ins = np.zeros(N, dtype=np.int64)
     for l in range(n_lib):
@@ -317,3 +318,79 @@ def hazard_batch(libs=None) -> ev.EvidenceBatch:
         off += nfr
     return ev.EvidenceBatch(np.array(sites, dtype=np.int32), np.array(frags, dtype=np.int32),
                             np.zeros((0, ev.SPLIT_WORDS), np.int32), libs)
+
+
+def concat_batches(parts, alloc=None, bucket=True) -> ev.EvidenceBatch:
+    """Concatenate site-disjoint batches (same library table) into one, fixing row offsets.
+
+    `alloc(name, shape, dtype)` may supply the destination arrays (e.g. pinned host
+    memory); default is plain numpy.
+    """
+    alloc = alloc or (lambda name, shape, dtype: np.empty(shape, dtype=dtype))
+    ns = sum(p.n_sites for p in parts)
+    nf = sum(p.n_frag for p in parts)
+    nsp = sum(p.n_split for p in parts)
+    sites = alloc("sites", (ns, ev.SITE_WORDS), np.int32)
+    frags = alloc("frags", (nf, ev.FRAG_WORDS), np.int32)
+    splits = alloc("splits", (nsp, ev.SPLIT_WORDS), np.int32)
+    s0 = f0 = p0 = 0
+    for p in parts:
+        s = p.sites.copy()
+        foff = s[:, 10:12].copy().view(np.int64).ravel() + f0
+        soff = s[:, 13:15].copy().view(np.int64).ravel() + p0
+        s[:, 10:12] = foff.view(np.int32).reshape(-1, 2)
+        s[:, 13:15] = soff.view(np.int32).reshape(-1, 2)
+        sites[s0:s0 + p.n_sites] = s
+        frags[f0:f0 + p.n_frag] = p.frags
+        splits[p0:p0 + p.n_split] = p.splits
+        s0, f0, p0 = s0 + p.n_sites, f0 + p.n_frag, p0 + p.n_split
+    out = ev.EvidenceBatch.__new__(ev.EvidenceBatch)
+    out.sites, out.frags, out.splits, out.libs, out.order = sites, frags, splits, parts[0].libs, None
+    if bucket:
+        order = alloc("order", (ns,), np.int32)
+        order[:] = out.length_order()
+        out.order = order
+    return out
+
+
+def _gen_chunk(args):
+    config, n, seed, stream, path = args
+    b = generate(config, n_sites=n, seed=seed, rank=stream, bucket=False)
+    if path is None:
+        return b.sites, b.frags, b.splits
+    np.save(path + ".sites.npy", b.sites)
+    np.save(path + ".frags.npy", b.frags)
+    np.save(path + ".splits.npy", b.splits)
+    return None
+
+
+def generate_parallel(config="del1m4lib", n_sites=None, rank=0, chunk=25_000, procs=None, alloc=None,
+                      bucket=True) -> ev.EvidenceBatch:
+    """`generate()` over independent Philox streams (one per chunk), fanned out over a
+    process pool; chunks travel through /dev/shm files, not pickles.  Stream ids are
+    `rank * 65536 + chunk_index`, so every rank of a multi-GPU job draws a distinct shard."""
+    import multiprocessing as mp
+    import tempfile
+    cfg = CONFIGS[config]
+    n = int(cfg["n_sites"] if n_sites is None else n_sites)
+    sizes = [min(chunk, n - i) for i in range(0, n, chunk)] or [0]
+    seed = BASE_SEED + cfg["seed_off"]
+    libs = make_libraries(cfg["n_lib"])
+    if len(sizes) == 1:
+        return concat_batches([generate(config, n_sites=sizes[0], seed=seed, rank=rank * 65536, bucket=False)],
+                              alloc, bucket)
+    procs = procs or min(len(sizes), max(1, (os.cpu_count() or 2) - 1), 32)
+    tmp = tempfile.mkdtemp(prefix="svgt_synth_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    jobs = [(config, sz, seed, rank * 65536 + i, os.path.join(tmp, "c%05d" % i)) for i, sz in enumerate(sizes)]
+    try:
+        with mp.get_context("forkserver").Pool(procs) as pool:
+            pool.map(_gen_chunk, jobs, chunksize=1)
+        parts = []
+        for j in jobs:
+            parts.append(ev.EvidenceBatch(np.load(j[4] + ".sites.npy", mmap_mode="r"),
+                                          np.load(j[4] + ".frags.npy", mmap_mode="r"),
+                                          np.load(j[4] + ".splits.npy", mmap_mode="r"), libs))
+        return concat_batches(parts, alloc, bucket)
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
