@@ -100,8 +100,9 @@ int svgt_launches_per_batch(const svgt_batch_t *batch);
 
 /*
  * Row-delivery variant of the scoring kernel (same results, different memory path):
- * 0 = per-lane 128-bit global loads with register prefetch, 1 = per-lane cp.async.bulk
- * (TMA 1-D) ring in shared memory.  -1 restores the built-in default (or the
+ * 0 = thread-per-site, per-lane 128-bit global loads with register prefetch; 1 = thread-per-site,
+ * per-lane cp.async.bulk (TMA 1-D) ring in shared memory; 2 = warp-cooperative (row per lane,
+ * ordered sums interleaved over 8 sites; the default).  -1 restores the default (or the
  * SVGT_VARIANT environment variable).  Returns the variant now in force.
  */
 int svgt_set_variant(int variant);

@@ -19,8 +19,10 @@
 enum {
     SVGT_VAR_DIRECT = 0,   /* per-lane LDG.128 x2 with register prefetch            */
     SVGT_VAR_BULK = 1,     /* per-lane cp.async.bulk (TMA 1-D) ring in shared memory */
-    SVGT_VAR_COUNT = 2
+    SVGT_VAR_COOP = 2,     /* warp-cooperative: row per lane, chains interleaved (svgt_coop.cu) */
+    SVGT_VAR_COUNT = 3
 };
+#define SVGT_COOP_THREADS 256       /* 8 warps per CTA in the cooperative kernel     */
 
 struct SvgtParams {
     const int4 *sites;  long long n_sites;
@@ -45,3 +47,4 @@ struct SvgtParams {
 /* Returns a cudaError_t as int.  `grid` <= 0 lets the launcher size a persistent grid. */
 int svgt_launch_score(const SvgtParams &p, int variant, cudaStream_t stream);
 size_t svgt_score_smem_bytes(const SvgtParams &p, int variant);
+int svgt_launch_coop(const SvgtParams &p, cudaStream_t stream);
