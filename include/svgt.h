@@ -101,8 +101,8 @@ int svgt_launches_per_batch(const svgt_batch_t *batch);
 /*
  * Row-delivery variant of the scoring kernel (same results, different memory path):
  * 0 = thread-per-site, per-lane 128-bit global loads with register prefetch; 1 = thread-per-site,
- * per-lane cp.async.bulk (TMA 1-D) ring in shared memory; 2 = warp-cooperative (row per lane,
- * ordered sums interleaved over 8 sites; the default).  -1 restores the default (or the
+ * per-lane cp.async.bulk (TMA 1-D) ring in shared memory; 2 / 3 = warp-cooperative (row per lane,
+ * ordered sums interleaved over 8 / 4 sites per warp; 2 is the default), tally + call kernels.  -1 restores the default (or the
  * SVGT_VARIANT environment variable).  Returns the variant now in force.
  */
 int svgt_set_variant(int variant);

@@ -85,7 +85,8 @@ int svgt_set_variant(int variant)
 int svgt_launches_per_batch(const svgt_batch_t *batch)
 {
     if (!batch) return fail(SVGT_ERR_ARG, "null batch%s", nullptr);
-    return batch->n_sites > 0 ? 1 : 0;
+    if (batch->n_sites <= 0) return 0;
+    return current_variant() >= SVGT_VAR_COOP ? 2 : 1;      /* tally + call kernels, or one fused kernel */
 }
 
 int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, void *stream)
@@ -116,7 +117,7 @@ int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, voi
     p.n_tiles = (int)((b->n_sites + 31) / 32);
     p.hist_in_smem = (b->n_hist <= SVGT_SMEM_HIST_WORDS) ? 1 : 0;
     const int variant = current_variant();
-    e = (cudaError_t)(variant == SVGT_VAR_COOP ? svgt_launch_coop(p, st) : svgt_launch_score(p, variant, st));
+    e = (cudaError_t)(variant >= SVGT_VAR_COOP ? svgt_launch_coop(p, variant, st) : svgt_launch_score(p, variant, st));
     if (e != cudaSuccess) return cuda_fail(e, "svgt_score_kernel launch");
     return SVGT_OK;
 }

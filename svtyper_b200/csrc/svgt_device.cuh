@@ -358,4 +358,12 @@ __device__ __forceinline__ void call_site(const SvgtParams &p, const Tables &t, 
 }
 
 
+/* coordinates the integer window arithmetic is exact for (SVGT_ERR_RANGE otherwise) */
+__device__ __forceinline__ bool site_fields_in_range(const int4 a, const int4 b, int m, int slop)
+{
+    auto ok = [](int v, int lim) { return v > -lim && v < lim; };
+    return ok(a.x, kRange) && ok(a.y, kRange) && ok(a.z, kCiRange) && ok(a.w, kCiRange) && ok(b.x, kCiRange) &&
+           ok(b.y, kCiRange) && m >= 0 && m < (1 << 20) && slop >= 0 && slop < (1 << 20);
+}
+
 }  // namespace

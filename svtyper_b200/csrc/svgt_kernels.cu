@@ -124,12 +124,6 @@ __device__ __forceinline__ void stream_rows(Ring &ring, const int4 *rows, int n,
     }
 }
 
-__device__ __forceinline__ bool site_in_range(const int4 a, const int4 b, int m, int slop)
-{
-    auto ok = [](int v, int lim) { return v > -lim && v < lim; };
-    return ok(a.x, kRange) && ok(a.y, kRange) && ok(a.z, kCiRange) && ok(a.w, kCiRange) && ok(b.x, kCiRange) &&
-           ok(b.y, kCiRange) && m >= 0 && m < (1 << 20) && slop >= 0 && slop < (1 << 20);
-}
 
 template <int VARIANT, int ASSOC>
 __global__ void __launch_bounds__(SVGT_THREADS, 4) svgt_score_kernel(const SvgtParams p)
@@ -183,7 +177,7 @@ __global__ void __launch_bounds__(SVGT_THREADS, 4) svgt_score_kernel(const SvgtP
         /* a = posA posB ciA0 ciA1 | b = ciB0 ciB1 tidA tidB | c = var_length meta foff.lo foff.hi | d = nf soff.lo soff.hi ns */
         const int meta = c.y;
         const bool skip = !valid || (meta & SITE_SKIP);
-        const bool ranged = site_in_range(a, b, m, slop);
+        const bool ranged = site_fields_in_range(a, b, m, slop);
         const bool run = !skip && ranged;
         const long long foff = ((long long)(unsigned)c.z) | ((long long)c.w << 32);
         const long long soff = ((long long)(unsigned)d.y) | ((long long)d.z << 32);

@@ -19,8 +19,9 @@
 enum {
     SVGT_VAR_DIRECT = 0,   /* per-lane LDG.128 x2 with register prefetch            */
     SVGT_VAR_BULK = 1,     /* per-lane cp.async.bulk (TMA 1-D) ring in shared memory */
-    SVGT_VAR_COOP = 2,     /* warp-cooperative: row per lane, chains interleaved (svgt_coop.cu) */
-    SVGT_VAR_COUNT = 3
+    SVGT_VAR_COOP = 2,     /* warp-cooperative, 8 sites interleaved per warp (svgt_coop.cu) */
+    SVGT_VAR_COOP4 = 3,    /* warp-cooperative, 4 sites interleaved per warp                 */
+    SVGT_VAR_COUNT = 4
 };
 #define SVGT_COOP_THREADS 256       /* 8 warps per CTA in the cooperative kernel     */
 
@@ -47,4 +48,4 @@ struct SvgtParams {
 /* Returns a cudaError_t as int.  `grid` <= 0 lets the launcher size a persistent grid. */
 int svgt_launch_score(const SvgtParams &p, int variant, cudaStream_t stream);
 size_t svgt_score_smem_bytes(const SvgtParams &p, int variant);
-int svgt_launch_coop(const SvgtParams &p, cudaStream_t stream);
+int svgt_launch_coop(const SvgtParams &p, int variant, cudaStream_t stream);
