@@ -9,7 +9,7 @@ B="python bench.py --sites $SITES --steps 3 --warmup 3 --no-cpu-baseline --e2e-s
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/launches_$TAG.out 2>&1
 echo "launch list rc=$?"
 for v in ${VARIANTS:-0 1}; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:svgt_ -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_v$v $B --variant $v > gpurun_out/prof_${TAG}_v$v.out 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX:-svgt_} -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_v$v $B --variant $v > gpurun_out/prof_${TAG}_v$v.out 2>&1
   echo "full capture v$v rc=$?"
 done
 ls -la gpurun_out
