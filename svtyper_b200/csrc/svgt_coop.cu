@@ -51,13 +51,14 @@ struct Win {
     unsigned recA_lo, recA_w1, recB_lo, recB_w1;
     unsigned rAa_lo, rAa_w1, rAb_lo, rAb_w1;
     unsigned rBa_lo, rBa_w1, rBb_lo, rBb_w1;
-};  /* 64 B */
+    unsigned pad[4];            /* 80 B stride: the four cached libraries land in distinct banks */
+};
 
 template <int G>
-struct WarpSmem {
+struct alignas(128) WarpSmem {
     SiteS site[G];
     Win win[G][kWLibs];
-    double contrib[G][32][4];
+    double contrib[G][33][4];   /* 32 rows + 32 B pad: chain lanes of different sites hit distinct banks */
     unsigned newmask[G];
     double zero[2];
 };
@@ -225,7 +226,6 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
             unsigned carryA = 0u, carryB = 0u;      /* EXTRA-run hits carried into the next step, bit g */
 
             /* chunk iterator (warp-uniform): (step, g) in step-major order over sites with rows left */
-            int it_step = 0, it_g = -1;
             auto advance = [&](int &st, int &g) -> bool {
                 for (;;) {
                     ++g;
@@ -241,18 +241,9 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     lo = ldg4(rp); hi = ldg4(rp + 1);
                 }
             };
-            int4 nlo, nhi;
-            bool more = nfmax > 0 && advance(it_step = 0, it_g = -1);
-            if (more) load_rows(it_step, it_g, nlo, nhi);
             bool all_new = true;
-            while (more) {
-                const int step = it_step, g = it_g;
-                const int4 lo = nlo, hi = nhi;
-                int nstep = step, ng = g;
-                more = advance(nstep, ng);
-                if (more) load_rows(nstep, ng, nlo, nhi);       /* next chunk in flight while this one is scored */
-                it_step = nstep; it_g = ng;
-
+            /* score one 32-row chunk (phase A); `flush` = last chunk of its super-step (phase B follows) */
+            auto process = [&](const int step, const int g, const int4 lo, const int4 hi, const bool flush) {
                 /* ---------------- phase A: score 32 rows of site g ---------------- */
                 const int4 s0 = *reinterpret_cast<const int4 *>(&ws.site[g].tA);   /* tA tB wA0 wA1 */
                 const int4 s1 = *reinterpret_cast<const int4 *>(&ws.site[g].wB0);  /* wB0 wB1 meta var_length */
@@ -313,7 +304,8 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 const bool slow = paired & libok & !fast;
                 const Win *wp = &ws.win[g][lib < kWLibs ? lib : 0];
                 const uint4 w0 = *reinterpret_cast<const uint4 *>(&wp->altA_lo);
-                const uint4 w1 = *reinterpret_cast<const uint4 *>(&wp->recA_lo);
+                uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
+                if ((smeta & 3) == SV_INV) w1 = *reinterpret_cast<const uint4 *>(&wp->recA_lo);
                 const uint4 w2 = *reinterpret_cast<const uint4 *>(&wp->rAa_lo);
                 const uint4 w3 = *reinterpret_cast<const uint4 *>(&wp->rBa_lo);
                 const int svtype = smeta & 3;
@@ -321,7 +313,9 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 const int st = (fl >> 2) & 3, o12 = (smeta >> 2) & 3;
                 const bool ab = ea & fb;
                 bool alt = fast & ab & (st == o12) & in_win(lo.x, w0.x, w0.y) & in_win(lo.w, w0.z, w0.w);
-                bool recip = fast & ab & (st == (o12 ^ 3)) & in_win(lo.x, w1.x, w1.y) & in_win(lo.w, w1.z, w1.w);
+                bool recip = false;
+                if (svtype == SV_INV)                               /* warp-uniform: one site per chunk */
+                    recip = fast & ab & (st == (o12 ^ 3)) & in_win(lo.x, w1.x, w1.y) & in_win(lo.w, w1.z, w1.w);
                 const bool fr = st == 2;                            /* readA forward, readB reverse */
                 bool refA = fast & fr & ea & fa & in_win(lo.x, w2.x, w2.y) & in_win(lo.w, w2.z, w2.w);
                 bool refB = fast & fr & eb & fb & in_win(lo.x, w3.x, w3.y) & in_win(lo.w, w3.z, w3.w);
@@ -382,7 +376,7 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 if (lane == 0) ws.newmask[g] = nm;
 
                 /* ---------------- phase B at the end of each super-step ---------------- */
-                if (!more || nstep != step) {
+                if (flush) {
                     __syncwarp();
                     if (gb < G && c < 3) {
                         int cnt = ws.site[gb].nf - step * 32;
@@ -395,6 +389,22 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     __syncwarp();
                     all_new = true;
                 }
+            };
+            /* two row buffers in registers: the next chunk is always in flight while one is scored */
+            int st0 = 0, g0 = -1;
+            int4 r0lo, r0hi, r1lo, r1hi;
+            bool more = nfmax > 0 && advance(st0, g0);
+            if (more) load_rows(st0, g0, r0lo, r0hi);
+            while (more) {
+                int st1 = st0, g1 = g0;
+                const bool m1 = advance(st1, g1);
+                if (m1) load_rows(st1, g1, r1lo, r1hi);
+                process(st0, g0, r0lo, r0hi, !m1 || st1 != st0);
+                if (!m1) break;
+                st0 = st1; g0 = g1;
+                more = advance(st0, g0);
+                if (more) load_rows(st0, g0, r0lo, r0hi);
+                process(st1, g1, r1lo, r1hi, !more || st0 != st1);
             }
             if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
             sum_frag = acc;
