@@ -51,7 +51,8 @@ struct Win {
     unsigned recA_lo, recA_w1, recB_lo, recB_w1;
     unsigned rAa_lo, rAa_w1, rAb_lo, rAb_w1;
     unsigned rBa_lo, rBa_w1, rBb_lo, rBb_w1;
-    unsigned pad[4];            /* 80 B stride: the four cached libraries land in distinct banks */
+    unsigned Lk, hist_off, hist_len, flags;   /* p_concordant inputs; flags bit 0 = integer fast path valid.
+                                                 80 B stride: the four cached libraries land in distinct banks */
 };
 
 template <int G>
@@ -69,7 +70,7 @@ __device__ __forceinline__ void set_win(unsigned &lo_out, unsigned &w1_out, int 
     w1_out = (enable && hi >= lo) ? (unsigned)(hi - lo) + 1u : 0u;
 }
 
-__device__ __forceinline__ Win make_win(const SiteS &S, const LibK &L, int m)
+__device__ __forceinline__ Win make_win(const SiteS &S, const LibK &L, int m, bool small_counts)
 {
     Win w;
     const int svtype = S.meta & 3;
@@ -88,13 +89,166 @@ __device__ __forceinline__ Win make_win(const SiteS &S, const LibK &L, int m)
     set_win(w.rAb_lo, w.rAb_w1, S.wA1 + 1, S.wA1 + 1 + FL, ok && !small_del);
     set_win(w.rBa_lo, w.rBa_w1, S.wB0 - FL, S.wB0, ok && !small_del);
     set_win(w.rBb_lo, w.rBb_w1, S.wB1 + 1, S.wB1 + 1 + FL, ok && !small_del);
+    /* second histogram key is o - Lk: Lk = var_length (DEL) or the integral mean+3sd (others);
+     * "no key" becomes 0x7fffffff, which no |b_end - a_start| of a straddling pair reaches */
+    const int Lk = is_del ? S.var_length : L.nondel_L;
+    w.Lk = (!is_del && Lk < 0) ? 0x7fffffffu : (unsigned)Lk;
+    w.hist_off = (unsigned)L.hist_off;
+    w.hist_len = (unsigned)L.hist_len;
+    w.flags = (ok && small_counts && !(is_del && Lk < 0)) ? 1u : 0u;
     return w;
+}
+
+/* everything the integer fast path does not cover, evaluated the long way for one row:
+ * libraries beyond the window cache or not provably integer-exact, histogram counts >= 2^26,
+ * breakends within min_aligned of the contig start, malformed DEL lengths, p_concordant ties */
+__device__ __noinline__ void slow_row(const SvgtParams &p, const Tables &t, const SiteS &S, const int4 lo,
+                                      const int4 hi, const LibK *s_lib, int m, int &err, bool &alt, bool &refA,
+                                      bool &refB, bool &pc)
+{
+    const int lib = (int)(((unsigned)hi.z) >> 16);
+    if (lib >= p.n_lib) { err = SVGT_ERR_LIB_INDEX; alt = refA = refB = pc = false; return; }
+    LibK Ls;
+    if (lib >= SVGT_SMEM_LIBS) { int e = 0; Ls = derive_lib(p, lib, &e); }
+    const LibK &L = (lib < SVGT_SMEM_LIBS) ? s_lib[lib] : Ls;
+    const int svtype = S.meta & 3;
+    const bool is_del = svtype == SV_DEL;
+    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1;
+    const bool small_del = is_del && ((double)((long long)S.posB - S.posA) < L.two_sd);
+    alt = !small_del && straddle_literal(lo, hi, S.tA, S.posA, S.ciA0, S.ciA1, S.tB, S.posB, S.ciB0, S.ciB1, o1, o2,
+                                         m, L.flank);
+    if (svtype == SV_INV)
+        alt = alt || straddle_literal(lo, hi, S.tA, S.posA, S.ciA0, S.ciA1, S.tB, S.posB, S.ciB0, S.ciB1, !o1, !o2, m,
+                                      L.flank);
+    refA = !small_del && straddle_literal(lo, hi, S.tA, S.posA, 0, 0, S.tA, S.posA, 0, 0, 0, 1, m, L.flank);
+    refB = !small_del && straddle_literal(lo, hi, S.tB, S.posB, 0, 0, S.tB, S.posB, 0, 0, 0, 1, m, L.flank);
+    pc = p_concordant(t, L, lo.x, lo.w, is_del, S.var_length);
 }
 
 __device__ __forceinline__ bool in_win(int v, unsigned lo, unsigned w1) { return ((unsigned)v - lo) < w1; }
 
-/* compact per-library ints for the row loop: {hist_off, hist_len, nondel_L, safe} */
-__device__ __forceinline__ int4 lib_quad(const LibK &L) { return make_int4(L.hist_off, L.hist_len, L.nondel_L, L.safe); }
+
+/*
+ * Predicate chains in PTX.  The C++ forms of these tests compile to an ISETP plus a SEL per
+ * boolean (every bool is materialised as 0/1 and recombined with LOP3); the kernel is ALU-pipe
+ * bound, so the chains are written with setp.<cmp>.and so one compare also ANDs in the running
+ * predicate.  All compares are exact for every int32 input (no subtract-and-test-sign tricks).
+ */
+
+/* is_ref_seq for both reads against both breakends (parsers.py:801-816), both windows valid */
+__device__ __forceinline__ void hits_chain(int a_start, int a_end, int b_start, int b_end, int tidA, int tidB, int fl,
+                                           int tA, int tB, int wA0, int wA1, int wB0, int wB1, int &hitA, int &hitB)
+{
+    asm("{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 t;\n\t"
+        "setp.le.s32 p, %2, %11;\n\t"
+        "setp.ge.and.s32 p, %3, %12, p;\n\t"
+        "setp.eq.and.s32 p, %6, %9, p;\n\t"
+        "setp.le.s32 q, %2, %13;\n\t"
+        "setp.ge.and.s32 q, %3, %14, q;\n\t"
+        "setp.eq.and.s32 q, %6, %10, q;\n\t"
+        "or.pred p, p, q;\n\t"
+        "and.b32 t, %8, 1;\n\t"
+        "setp.ne.and.s32 p, t, 0, p;\n\t"
+        "selp.s32 %0, 1, 0, p;\n\t"
+        "setp.le.s32 p, %4, %11;\n\t"
+        "setp.ge.and.s32 p, %5, %12, p;\n\t"
+        "setp.eq.and.s32 p, %7, %9, p;\n\t"
+        "setp.le.s32 q, %4, %13;\n\t"
+        "setp.ge.and.s32 q, %5, %14, q;\n\t"
+        "setp.eq.and.s32 q, %7, %10, q;\n\t"
+        "or.pred p, p, q;\n\t"
+        "and.b32 t, %8, 2;\n\t"
+        "setp.ne.and.s32 p, t, 0, p;\n\t"
+        "selp.s32 %1, 1, 0, p;\n\t"
+        "}"
+        : "=r"(hitA), "=r"(hitB)
+        : "r"(a_start), "r"(a_end), "r"(b_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(fl), "r"(tA), "r"(tB),
+          "r"(wA0), "r"(wA1), "r"(wB0), "r"(wB1));
+}
+
+/*
+ * is_pair_straddle x3 (alt, ref at A, ref at B; parsers.py:821-857 through the per-(site, library)
+ * windows), p_concordant as 19*h1 > h2 on the histogram counts (parsers.py:861-882)
+ * and the selection of the prob_mapq LUT indices that realise
+ *     p_alt = alt ? (DEL & p_conc ? 0 : pmA * pmB) : 0            singlesample.py:305-318
+ *     p_ref = (refA | refB) & (!(refA & refB) | DEL) & p_conc ? pmA * pmB * (refA + refB) / 2 : 0   :336-350
+ * Outputs LUT indices (0 selects pm[0] == 0.0; +256 selects the halved table) and a `tie` flag
+ * (19*h1 == h2 != 0: the caller evaluates the literal fp64 expression).
+ */
+__device__ __forceinline__ void pe_chain(int a_start, int b_end, int tidA, int tidB, int st, int fastflag,
+                                         int tA, int tB, int o12, int is_del, uint4 w0, uint4 w2, uint4 w3,
+                                         unsigned Lk, unsigned hist_off, unsigned hist_len, const unsigned *hist,
+                                         int mqA, int mqB, int &idx_alt, int &idx_ref, int &idx_refB, int &tie,
+                                         int &alt_out)
+{
+    asm("{\n\t"
+        ".reg .pred pf, pa, pfr, ra, rb, p1, p2, pc, pt, pboth, pany, pdel, pron, paon;\n\t"
+        ".reg .b32 d, o, k2, h1, h2, l19, t;\n\t"
+        ".reg .b64 ad;\n\t"
+        "setp.ne.s32 pf, %10, 0;\n\t"
+        /* alt: tids (A on A, B on B), strands, both windows */
+        "setp.eq.and.s32 pa, %7, %11, pf;\n\t"
+        "setp.eq.and.s32 pa, %8, %12, pa;\n\t"
+        "setp.eq.and.s32 pa, %9, %13, pa;\n\t"
+        "sub.s32 d, %5, %15;\n\t"
+        "setp.lt.and.u32 pa, d, %16, pa;\n\t"
+        "sub.s32 d, %6, %17;\n\t"
+        "setp.lt.and.u32 pa, d, %18, pa;\n\t"
+        /* reference-spanning pairs are forward/reverse (st == 2) */
+        "setp.eq.and.s32 pfr, %9, 2, pf;\n\t"
+        "setp.eq.and.s32 ra, %7, %11, pfr;\n\t"
+        "setp.eq.and.s32 ra, %8, %11, ra;\n\t"
+        "sub.s32 d, %5, %19;\n\t"
+        "setp.lt.and.u32 ra, d, %20, ra;\n\t"
+        "sub.s32 d, %6, %21;\n\t"
+        "setp.lt.and.u32 ra, d, %22, ra;\n\t"
+        "setp.eq.and.s32 rb, %7, %12, pfr;\n\t"
+        "setp.eq.and.s32 rb, %8, %12, rb;\n\t"
+        "sub.s32 d, %5, %23;\n\t"
+        "setp.lt.and.u32 rb, d, %24, rb;\n\t"
+        "sub.s32 d, %6, %25;\n\t"
+        "setp.lt.and.u32 rb, d, %26, rb;\n\t"
+        /* p_concordant on counts: h1 = hist[o], h2 = hist[o - Lk] (missing keys are 0) */
+        "sad.s32 o, %6, %5, 0;\n\t"
+        "sub.s32 k2, o, %27;\n\t"
+        "mov.b32 h1, 0;\n\t"
+        "mov.b32 h2, 0;\n\t"
+        "setp.lt.and.u32 p1, o, %29, pf;\n\t"
+        "setp.lt.and.u32 p2, k2, %29, pf;\n\t"
+        "add.s32 t, o, %28;\n\t"
+        "mad.wide.u32 ad, t, 4, %30;\n\t"
+        "@p1 ld.u32 h1, [ad];\n\t"
+        "add.s32 t, k2, %28;\n\t"
+        "mad.wide.u32 ad, t, 4, %30;\n\t"
+        "@p2 ld.u32 h2, [ad];\n\t"
+        "mul.lo.u32 l19, h1, 19;\n\t"
+        "setp.gt.u32 pc, l19, h2;\n\t"
+        "setp.eq.u32 pt, l19, h2;\n\t"
+        "setp.ne.and.u32 pt, h2, 0, pt;\n\t"
+        "selp.s32 %3, 1, 0, pt;\n\t"
+        /* weights */
+        "setp.ne.s32 pdel, %14, 0;\n\t"
+        "and.pred pboth, ra, rb;\n\t"
+        "or.pred pany, ra, rb;\n\t"
+        "and.pred p1, pboth, !pdel;\n\t"         /* both sides straddled on a non-DEL: no ref evidence */
+        "and.pred pron, pany, !p1;\n\t"
+        "and.pred pron, pron, pc;\n\t"
+        "and.pred p2, pdel, pc;\n\t"
+        "and.pred paon, pa, !p2;\n\t"
+        "selp.s32 %0, %31, 0, paon;\n\t"
+        "selp.s32 %1, %31, 0, pron;\n\t"
+        "add.s32 t, %32, 256;\n\t"
+        "selp.s32 %2, %32, t, pboth;\n\t"
+        "selp.s32 %4, 1, 0, pa;\n\t"
+        "}"
+        : "=r"(idx_alt), "=r"(idx_ref), "=r"(idx_refB), "=r"(tie), "=r"(alt_out)
+        : "r"(a_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(st), "r"(fastflag), "r"(tA), "r"(tB), "r"(o12),
+          "r"(is_del), "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w2.x), "r"(w2.y), "r"(w2.z), "r"(w2.w),
+          "r"(w3.x), "r"(w3.y), "r"(w3.z), "r"(w3.w), "r"(Lk), "r"(hist_off), "r"(hist_len), "l"(hist), "r"(mqA),
+          "r"(mqB));
+}
 
 /* ordered replay of one chain over `cnt` parked rows (phase B).
  * SSO:     per row   if NEW: acc += pend, pend = 0;   pend = (pend + x) + y
@@ -135,9 +289,8 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
     typedef WarpSmem<G> WS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_pm = reinterpret_cast<double *>(smem_raw);
-    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 256);
-    int4 *s_libq = reinterpret_cast<int4 *>(s_lib + SVGT_SMEM_LIBS);
-    size_t off = 256 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * (sizeof(LibK) + sizeof(int4));
+    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 512);     /* pm[0..255], then pm[q] / 2 */
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
     off = (off + 127) & ~(size_t)127;
     WS *s_warp = reinterpret_cast<WS *>(smem_raw + off);
     off += sizeof(WS) * kCoopWarps;
@@ -147,24 +300,28 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
     const unsigned full = 0xffffffffu;
     int err = 0;
     const int nl = p.n_lib < SVGT_SMEM_LIBS ? p.n_lib : SVGT_SMEM_LIBS;
-    for (int i = tid; i < 256; i += SVGT_COOP_THREADS) s_pm[i] = p.pm[i];
-    for (int i = tid; i < nl; i += SVGT_COOP_THREADS) {
-        const LibK k = derive_lib(p, i, &err);
-        s_lib[i] = k;
-        s_libq[i] = lib_quad(k);
+    for (int i = tid; i < 256; i += SVGT_COOP_THREADS) {
+        const double v = p.pm[i];
+        s_pm[i] = v;
+        s_pm[256 + i] = __dmul_rn(v, 0.5);
     }
-    if (p.hist_in_smem)
-        for (int i = tid; i < (int)p.n_hist; i += SVGT_COOP_THREADS) s_hist[i] = p.hist[i];
+    for (int i = tid; i < nl; i += SVGT_COOP_THREADS) s_lib[i] = derive_lib(p, i, &err);
+    /* the 32-bit form of 19*h1 > h2 needs every histogram count below 2^26 */
+    int big = 0;
+    for (long long i = tid; i < p.n_hist; i += SVGT_COOP_THREADS) {
+        const unsigned v = p.hist[i];
+        if (p.hist_in_smem) s_hist[i] = v;
+        big |= v >= (1u << 26);
+    }
     WS &ws = s_warp[warp];
     if (lane < 2) ws.zero[lane] = 0.0;
-    __syncthreads();
+    const bool small_counts = __syncthreads_or(big) == 0;
 
     Tables t;
     t.pm = s_pm; t.libs = s_lib; t.hist = p.hist_in_smem ? s_hist : p.hist;
     t.conc = p.consts[C_CONC]; t.disc = p.consts[C_DISC];
     const unsigned *hist = t.hist;
     const int m = p.min_aligned, slop = p.split_slop;
-    const int n_lib = p.n_lib;
 
     /* phase-B role of this lane: chain c of interleaved site gb */
     const int gb = lane >> 2, c = lane & 3;
@@ -209,7 +366,8 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
             __syncwarp();
             for (int i = lane; i < G * kWLibs; i += 32) {
                 const int g = i / kWLibs, l = i % kWLibs;
-                if (l < nl && (ws.site[g].nf | ws.site[g].ns)) ws.win[g][l] = make_win(ws.site[g], s_lib[l], m);
+                if (l < nl) { if (ws.site[g].nf) ws.win[g][l] = make_win(ws.site[g], s_lib[l], m, small_counts); }
+                else ws.win[g][l].flags = 0u;
             }
             __syncwarp();
         }
@@ -219,19 +377,24 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
 
         /* ================= fragment rows ================= */
         {
-            int nfmax = 0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) nfmax = max(nfmax, ws.site[g].nf);
             double acc = 0.0, pend = 0.0;
             unsigned carryA = 0u, carryB = 0u;      /* EXTRA-run hits carried into the next step, bit g */
+            bool all_new = true;
+            const int my_nf = lane < G ? ws.site[lane].nf : 0;
 
-            /* chunk iterator (warp-uniform): (step, g) in step-major order over sites with rows left */
+            /* chunk iterator (warp-uniform): step-major over the sites that still have rows */
+            int it_step = -1;
+            unsigned it_mask = 0u;
             auto advance = [&](int &st, int &g) -> bool {
-                for (;;) {
-                    ++g;
-                    if (g >= G) { g = 0; ++st; if (st * 32 >= nfmax) return false; }
-                    if (ws.site[g].nf > st * 32) return true;
+                if (it_mask == 0u) {
+                    ++it_step;
+                    it_mask = __ballot_sync(full, my_nf > it_step * 32);
+                    if (it_mask == 0u) return false;
                 }
+                g = __ffs(it_mask) - 1;
+                it_mask &= it_mask - 1u;
+                st = it_step;
+                return true;
             };
             auto load_rows = [&](int st, int g, int4 &lo, int4 &hi) {
                 const int n = ws.site[g].nf - st * 32;
@@ -241,28 +404,55 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     lo = ldg4(rp); hi = ldg4(rp + 1);
                 }
             };
-            bool all_new = true;
             /* score one 32-row chunk (phase A); `flush` = last chunk of its super-step (phase B follows) */
             auto process = [&](const int step, const int g, const int4 lo, const int4 hi, const bool flush) {
-                /* ---------------- phase A: score 32 rows of site g ---------------- */
+#ifdef SVGT_MARK
+                asm volatile("membar.cta;" ::: "memory");
+#endif
                 const int4 s0 = *reinterpret_cast<const int4 *>(&ws.site[g].tA);   /* tA tB wA0 wA1 */
                 const int4 s1 = *reinterpret_cast<const int4 *>(&ws.site[g].wB0);  /* wB0 wB1 meta var_length */
-                const int n = min(32, ws.site[g].nf - step * 32);
+                const int n = ws.site[g].nf - step * 32;
                 const bool rv = lane < n;
-                const unsigned vm = n == 32 ? full : ((1u << n) - 1u);
+                const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
                 const int fl = rv ? hi.w : 0;
                 const int smeta = s1.z;
-                const bool okA = (smeta >> 8) & 1, okB = (smeta >> 9) & 1;
-                const bool ea = hi.x == s0.x, eb = hi.x == s0.y, fa = hi.y == s0.x, fb = hi.y == s0.y;
-                const bool cAA = (lo.x <= s0.z) & (lo.y >= s0.w), cAB = (lo.x <= s1.x) & (lo.y >= s1.y);
-                const bool cBA = (lo.z <= s0.z) & (lo.w >= s0.w), cBB = (lo.z <= s1.x) & (lo.w >= s1.y);
-                bool hitA = ((fl & F_HAS_A) != 0) & ((ea & okA & cAA) | (eb & okB & cAB));
-                bool hitB = ((fl & F_HAS_B) != 0) & ((fa & okA & cBA) | (fb & okB & cBB));
+                const int svtype = smeta & 3;
+                const bool is_del = svtype == SV_DEL;
+                /* the PTX chains cover sites whose two ref-seq windows are valid and that are not INV
+                 * (reciprocal orientation); everything else takes the same tests in C++ (site-uniform) */
+                const bool common = ((smeta >> 8) & 3) == 3 && svtype != SV_INV;
+                const int mqA = hi.z & 0xFF, mqB = (hi.z >> 8) & 0xFF;
+                const unsigned lib = ((unsigned)hi.z) >> 16;
                 const bool isx = (fl & F_EXTRA) != 0;
+                const bool paired = ((fl & F_PAIRED) != 0) & !isx;
+                const Win *wp = &ws.win[g][lib < (unsigned)kWLibs ? lib : 0u];
+                const uint4 w4 = *reinterpret_cast<const uint4 *>(&wp->Lk);          /* Lk hist_off hist_len flags */
+                const bool fast = paired & (lib < (unsigned)kWLibs) & ((w4.w & 1u) != 0u);
+                const uint4 w0 = *reinterpret_cast<const uint4 *>(&wp->altA_lo);
+                const uint4 w2 = *reinterpret_cast<const uint4 *>(&wp->rAa_lo);
+                const uint4 w3 = *reinterpret_cast<const uint4 *>(&wp->rBa_lo);
+                const int st = (fl >> 2) & 3, o12 = (smeta >> 2) & 3;
+
+                /* ---- is_ref_seq hits (parsers.py:801-816) ---- */
+                int hitA, hitB;
+                if (common) {
+                    hits_chain(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, fl, s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, hitA, hitB);
+                } else {
+                    const bool okA = (smeta >> 8) & 1, okB = (smeta >> 9) & 1;
+                    const bool ea = hi.x == s0.x, eb = hi.x == s0.y, fa = hi.y == s0.x, fb = hi.y == s0.y;
+                    hitA = ((fl & F_HAS_A) != 0) && ((ea && okA && lo.x <= s0.z && lo.y >= s0.w) ||
+                                                     (eb && okB && lo.x <= s1.x && lo.y >= s1.y));
+                    hitB = ((fl & F_HAS_B) != 0) && ((fa && okA && lo.z <= s0.z && lo.w >= s0.w) ||
+                                                     (fb && okB && lo.z <= s1.x && lo.w >= s1.y));
+                }
                 /* EXTRA interval rows feed the next main row's MULTI slots (evidence.py) */
-                const unsigned XM = __ballot_sync(full, (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B)) != 0);
-                const bool cA = (carryA >> g) & 1u, cB = (carryB >> g) & 1u;
-                if (XM != 0u || cA || cB) {
+                const unsigned XM = __ballot_sync(full, (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B | F_CONT)) != 0);
+                unsigned nm = vm;
+                if (XM != 0u || ((carryA | carryB) >> g) & 1u) {
+#ifdef SVGT_MARK
+                    asm volatile("membar.cta;" ::: "memory");
+#endif
+                    const bool cA = (carryA >> g) & 1u, cB = (carryB >> g) & 1u;
                     const unsigned E = __ballot_sync(full, isx);
                     const unsigned HA = __ballot_sync(full, isx && hitA), HB = __ballot_sync(full, isx && hitB);
                     const unsigned below = (1u << lane) - 1u;
@@ -285,95 +475,67 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     }
                     carryA = (carryA & ~(1u << g)) | ((unsigned)nA << g);
                     carryB = (carryB & ~(1u << g)) | ((unsigned)nB << g);
+                    nm = __ballot_sync(full, rv && !(fl & (F_CONT | F_EXTRA)));
+                    all_new = all_new && (nm == vm);
+                    if (isx) { hitA = 0; hitB = 0; }
+#ifdef SVGT_MARK
+                    asm volatile("membar.cta;" ::: "memory");
+#endif
                 }
-                const unsigned nm = __ballot_sync(full, rv && !(fl & (F_CONT | F_EXTRA)));
-                all_new = all_new && (nm == vm);
 
-                const double pmA = s_pm[hi.z & 0xFF], pmB = s_pm[(hi.z >> 8) & 0xFF];
-                const int lib = (hi.z >> 16) & 0xFFFF;
-                const double va = (!isx & ((fl & F_HAS_A) != 0) & hitA) ? pmA : 0.0;
-                const double vb = (!isx & ((fl & F_HAS_B) != 0) & hitB) ? pmB : 0.0;
-
-                /* paired-end evidence, branch-free on the common path (safe library with cached windows) */
-                const bool paired = ((fl & F_PAIRED) != 0) & !isx;
-                const bool libok = lib < n_lib;
-                if (paired & !libok) err = SVGT_ERR_LIB_INDEX;
-                const int libc = lib < nl ? lib : 0;
-                const int4 lq = s_libq[libc];                       /* hist_off hist_len nondel_L safe */
-                const bool fast = paired & libok & (lib < kWLibs) & (lq.w != 0);
-                const bool slow = paired & libok & !fast;
-                const Win *wp = &ws.win[g][lib < kWLibs ? lib : 0];
-                const uint4 w0 = *reinterpret_cast<const uint4 *>(&wp->altA_lo);
-                uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
-                if ((smeta & 3) == SV_INV) w1 = *reinterpret_cast<const uint4 *>(&wp->recA_lo);
-                const uint4 w2 = *reinterpret_cast<const uint4 *>(&wp->rAa_lo);
-                const uint4 w3 = *reinterpret_cast<const uint4 *>(&wp->rBa_lo);
-                const int svtype = smeta & 3;
-                const bool is_del = svtype == SV_DEL;
-                const int st = (fl >> 2) & 3, o12 = (smeta >> 2) & 3;
-                const bool ab = ea & fb;
-                bool alt = fast & ab & (st == o12) & in_win(lo.x, w0.x, w0.y) & in_win(lo.w, w0.z, w0.w);
-                bool recip = false;
-                if (svtype == SV_INV)                               /* warp-uniform: one site per chunk */
-                    recip = fast & ab & (st == (o12 ^ 3)) & in_win(lo.x, w1.x, w1.y) & in_win(lo.w, w1.z, w1.w);
-                const bool fr = st == 2;                            /* readA forward, readB reverse */
-                bool refA = fast & fr & ea & fa & in_win(lo.x, w2.x, w2.y) & in_win(lo.w, w2.z, w2.w);
-                bool refB = fast & fr & eb & fb & in_win(lo.x, w3.x, w3.y) & in_win(lo.w, w3.z, w3.w);
-                /* integer p_concordant: 19*h1 > h2; ties and unsafe libraries below */
-                const unsigned o = lo.w >= lo.x ? (unsigned)lo.w - (unsigned)lo.x : (unsigned)lo.x - (unsigned)lo.w;
-                const unsigned hl = (unsigned)lq.y;
-                const int Lk = is_del ? s1.w : lq.z;
-                const unsigned k2 = o - (unsigned)Lk;
-                const bool h1ok = paired & (o < hl);
-                const bool h2ok = paired & (Lk >= 0) & (o >= (unsigned)Lk) & (k2 < hl);
-                const unsigned h1 = h1ok ? hist[lq.x + o] : 0u;
-                const unsigned h2 = h2ok ? hist[lq.x + k2] : 0u;
-                const unsigned long long l19 = 19ull * h1;
-                bool pc = l19 > (unsigned long long)h2;
-                const bool tie = fast & (l19 == (unsigned long long)h2) & (h1 != 0u);
-                const bool negL = fast & (Lk < 0) & is_del;         /* malformed DEL: var_length < 0 */
-                if (__any_sync(full, slow | tie | negL)) {
-                    if (slow | tie | negL) {
-                        LibK Ls;
-                        if (lib >= SVGT_SMEM_LIBS) { int e = 0; Ls = derive_lib(p, lib, &e); }
-                        const LibK &L = (lib < SVGT_SMEM_LIBS) ? s_lib[lib] : Ls;
-                        const SiteS &S = ws.site[g];
-                        if (slow) {
-                            if (L.safe) {
-                                const Win w = make_win(S, L, m);
-                                alt = ab & (st == o12) & in_win(lo.x, w.altA_lo, w.altA_w1) & in_win(lo.w, w.altB_lo, w.altB_w1);
-                                recip = ab & (st == (o12 ^ 3)) & in_win(lo.x, w.recA_lo, w.recA_w1) &
-                                        in_win(lo.w, w.recB_lo, w.recB_w1);
-                                refA = fr & ea & fa & in_win(lo.x, w.rAa_lo, w.rAa_w1) & in_win(lo.w, w.rAb_lo, w.rAb_w1);
-                                refB = fr & eb & fb & in_win(lo.x, w.rBa_lo, w.rBa_w1) & in_win(lo.w, w.rBb_lo, w.rBb_w1);
-                            } else {
-                                const int o1 = (smeta >> 2) & 1, o2 = (smeta >> 3) & 1;
-                                const bool small_del = is_del && ((double)((long long)S.posB - S.posA) < L.two_sd);
-                                alt = !small_del && straddle_literal(lo, hi, S.tA, S.posA, S.ciA0, S.ciA1, S.tB, S.posB,
-                                                                     S.ciB0, S.ciB1, o1, o2, m, L.flank);
-                                recip = false;
-                                if (svtype == SV_INV)
-                                    recip = straddle_literal(lo, hi, S.tA, S.posA, S.ciA0, S.ciA1, S.tB, S.posB, S.ciB0,
-                                                             S.ciB1, !o1, !o2, m, L.flank);
-                                refA = !small_del && straddle_literal(lo, hi, S.tA, S.posA, 0, 0, S.tA, S.posA, 0, 0, 0, 1, m, L.flank);
-                                refB = !small_del && straddle_literal(lo, hi, S.tB, S.posB, 0, 0, S.tB, S.posB, 0, 0, 0, 1, m, L.flank);
-                            }
-                        }
-                        pc = p_concordant(t, L, lo.x, lo.w, is_del, s1.w);
+                /* ---- paired-end evidence -> LUT indices ---- */
+                /* weights as prob_mapq LUT indices: entry 0 is exactly 0.0, entries 256.. are halved */
+                auto weights = [&](bool alt, bool refA, bool refB, bool pc, int &ia, int &ir, int &irB) {
+                    const bool both = refA & refB;
+                    const bool ref_on = (refA | refB) & (!both | is_del) & pc;
+                    const bool alt_on = alt & !(is_del & pc);
+                    ia = alt_on ? mqA : 0; ir = ref_on ? mqA : 0; irB = mqB + (both ? 0 : 256);
+                };
+                int idx_alt, idx_ref, idx_refB, tie = 0;
+                if (common) {
+                    int alt_i;
+                    pe_chain(lo.x, lo.w, hi.x, hi.y, st, (int)fast, s0.x, s0.y, o12, (int)is_del, w0, w2, w3, w4.x, w4.y,
+                             w4.z, hist, mqA, mqB, idx_alt, idx_ref, idx_refB, tie, alt_i);
+                } else {
+                    const bool ea = hi.x == s0.x, eb = hi.x == s0.y, fa = hi.y == s0.x, fb = hi.y == s0.y;
+                    const bool ab = ea & fb & fast;
+                    bool alt = ab & (st == o12) & in_win(lo.x, w0.x, w0.y) & in_win(lo.w, w0.z, w0.w);
+                    if (svtype == SV_INV) {
+                        const uint4 w1 = *reinterpret_cast<const uint4 *>(&wp->recA_lo);
+                        alt |= ab & (st == (o12 ^ 3)) & in_win(lo.x, w1.x, w1.y) & in_win(lo.w, w1.z, w1.w);
+                    }
+                    const bool fr = (st == 2) & fast;
+                    const bool refA = fr & ea & fa & in_win(lo.x, w2.x, w2.y) & in_win(lo.w, w2.z, w2.w);
+                    const bool refB = fr & eb & fb & in_win(lo.x, w3.x, w3.y) & in_win(lo.w, w3.z, w3.w);
+                    const unsigned o = __sad(lo.w, lo.x, 0u);
+                    const unsigned k2 = o - w4.x;
+                    const unsigned h1 = (fast & (o < w4.z)) ? hist[w4.y + o] : 0u;
+                    const unsigned h2 = (fast & (k2 < w4.z)) ? hist[w4.y + k2] : 0u;
+                    const unsigned l19 = 19u * h1;
+                    tie = (l19 == h2) & (h2 != 0u);
+                    weights(alt, refA, refB, l19 > h2, idx_alt, idx_ref, idx_refB);
+                }
+                const bool slow = paired & !fast;
+                if (__any_sync(full, slow | (tie != 0))) {
+                    if (slow | (tie != 0)) {
+                        bool alt, refA, refB, pc;
+                        slow_row(p, t, ws.site[g], lo, hi, s_lib, m, err, alt, refA, refB, pc);
+                        weights(alt, refA, refB, pc, idx_alt, idx_ref, idx_refB);
                     }
                 }
-                const bool is_alt = alt | recip;
-                const bool use_ref = (refA | refB) & (!(refA & refB) | is_del);
-                const double prod = __dmul_rn(pmA, pmB);
-                /* singlesample.py:305-318: DEL alt weight is (1 - p_conc), p_conc a boolean;
-                 * :336-350: (refA + refB) * p_ref / 2.  Factors 0, 0.5, 1 multiply exactly. */
-                const int f_alt = (is_alt & !(is_del & pc)) ? 0x3FF00000 : 0;
-                const int f_ref = (use_ref & pc) ? ((refA & refB) ? 0x3FF00000 : 0x3FE00000) : 0;
-                const double p_alt = __dmul_rn(prod, __hiloint2double(f_alt, 0));
-                const double p_ref = __dmul_rn(prod, __hiloint2double(f_ref, 0));
+                /* singlesample.py:254-259: a = pm[A] if readA covers a breakend; :305-350: p_alt, p_ref.
+                 * 0.0 * x = 0.0 and the exact halving keep these bit-identical to the reference forms */
+                const double va = s_pm[hitA ? mqA : 0];
+                const double vb = s_pm[hitB ? mqB : 0];
+                const double pmB = s_pm[mqB];
+                const double p_alt = __dmul_rn(s_pm[idx_alt], pmB);
+                const double p_ref = __dmul_rn(s_pm[idx_ref], s_pm[idx_refB]);
                 double4 *dst = reinterpret_cast<double4 *>(&ws.contrib[g][lane][0]);
                 *dst = make_double4(va, vb, p_ref, p_alt);
                 if (lane == 0) ws.newmask[g] = nm;
+#ifdef SVGT_MARK
+                asm volatile("membar.cta;" ::: "memory");
+#endif
 
                 /* ---------------- phase B at the end of each super-step ---------------- */
                 if (flush) {
@@ -391,17 +553,16 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 }
             };
             /* two row buffers in registers: the next chunk is always in flight while one is scored */
-            int st0 = 0, g0 = -1;
+            int st0 = 0, g0 = 0;
             int4 r0lo, r0hi, r1lo, r1hi;
-            bool more = nfmax > 0 && advance(st0, g0);
+            bool more = advance(st0, g0);
             if (more) load_rows(st0, g0, r0lo, r0hi);
             while (more) {
-                int st1 = st0, g1 = g0;
+                int st1 = 0, g1 = 0;
                 const bool m1 = advance(st1, g1);
                 if (m1) load_rows(st1, g1, r1lo, r1hi);
                 process(st0, g0, r0lo, r0hi, !m1 || st1 != st0);
                 if (!m1) break;
-                st0 = st1; g0 = g1;
                 more = advance(st0, g0);
                 if (more) load_rows(st0, g0, r0lo, r0hi);
                 process(st1, g1, r1lo, r1hi, !more || st0 != st1);
@@ -533,7 +694,7 @@ __global__ void __launch_bounds__(256) svgt_call_kernel(const SvgtParams p)
 template <int G>
 size_t coop_smem_bytes(const SvgtParams &p)
 {
-    size_t off = 256 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * (sizeof(LibK) + sizeof(int4));
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
     off = (off + 127) & ~(size_t)127;
     off += sizeof(WarpSmem<G>) * kCoopWarps;
     if (p.hist_in_smem) off += (size_t)p.n_hist * sizeof(unsigned);
