@@ -127,6 +127,8 @@ __device__ __noinline__ void slow_row(const SvgtParams &p, const Tables &t, cons
 
 __device__ __forceinline__ bool in_win(int v, unsigned lo, unsigned w1) { return ((unsigned)v - lo) < w1; }
 
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 
 /*
  * Predicate chains in PTX.  The C++ forms of these tests compile to an ISETP plus a SEL per
@@ -372,6 +374,14 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
             __syncwarp();
         }
 
+        /* pull the first 1 KB of every site's fragment and split rows towards L2 now; later steps
+         * prefetch one super-step (G chunks) ahead of the register loads */
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (lane < ws.site[g].nf) prefetch_l2(p.frags + 2 * (ws.site[g].foff + lane));
+            if (lane < ws.site[g].ns) prefetch_l2(p.splits + 2 * (ws.site[g].soff + lane));
+        }
+
         double sum_frag = 0.0;      /* lane 4g+c: chain c of the fragment rows of site g */
         double sum_split = 0.0;     /* lane 4g+c: chain c of the split rows of site g    */
 
@@ -413,6 +423,7 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 const int4 s1 = *reinterpret_cast<const int4 *>(&ws.site[g].wB0);  /* wB0 wB1 meta var_length */
                 const int n = ws.site[g].nf - step * 32;
                 const bool rv = lane < n;
+                if (lane + 32 < n) prefetch_l2(p.frags + 2 * (ws.site[g].foff + (long long)step * 32 + 32 + lane));
                 const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
                 const int fl = rv ? hi.w : 0;
                 const int smeta = s1.z;
@@ -552,20 +563,26 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     all_new = true;
                 }
             };
-            /* two row buffers in registers: the next chunk is always in flight while one is scored */
-            int st0 = 0, g0 = 0;
-            int4 r0lo, r0hi, r1lo, r1hi;
-            bool more = advance(st0, g0);
-            if (more) load_rows(st0, g0, r0lo, r0hi);
-            while (more) {
-                int st1 = 0, g1 = 0;
-                const bool m1 = advance(st1, g1);
-                if (m1) load_rows(st1, g1, r1lo, r1hi);
-                process(st0, g0, r0lo, r0hi, !m1 || st1 != st0);
-                if (!m1) break;
-                more = advance(st0, g0);
-                if (more) load_rows(st0, g0, r0lo, r0hi);
-                process(st1, g1, r1lo, r1hi, !more || st0 != st1);
+            /* three row buffers in registers: two chunks are always in flight while one is scored */
+            int cs[3] = {0, 0, 0}, cg[3] = {0, 0, 0};
+            bool ok[3];
+            int4 rl[3], rh[3];
+            ok[0] = advance(cs[0], cg[0]);
+            if (ok[0]) load_rows(cs[0], cg[0], rl[0], rh[0]);
+            ok[1] = ok[0] && advance(cs[1], cg[1]);
+            if (ok[1]) load_rows(cs[1], cg[1], rl[1], rh[1]);
+            while (ok[0]) {
+                ok[2] = ok[1] && advance(cs[2], cg[2]);
+                if (ok[2]) load_rows(cs[2], cg[2], rl[2], rh[2]);
+                process(cs[0], cg[0], rl[0], rh[0], !ok[1] || cs[1] != cs[0]);
+                if (!ok[1]) break;
+                ok[0] = ok[2] && advance(cs[0], cg[0]);
+                if (ok[0]) load_rows(cs[0], cg[0], rl[0], rh[0]);
+                process(cs[1], cg[1], rl[1], rh[1], !ok[2] || cs[2] != cs[1]);
+                if (!ok[2]) break;
+                ok[1] = ok[0] && advance(cs[1], cg[1]);
+                if (ok[1]) load_rows(cs[1], cg[1], rl[1], rh[1]);
+                process(cs[2], cg[2], rl[2], rh[2], !ok[0] || cs[0] != cs[2]);
             }
             if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
             sum_frag = acc;
@@ -577,18 +594,29 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
 #pragma unroll
             for (int g = 0; g < G; ++g) nsmax = max(nsmax, ws.site[g].ns);
             double acc = 0.0, pend = 0.0;
+            auto load_split = [&](int step, int g, int4 &q0, int4 &q1) {
+                q0 = make_int4(0, 0, 0, 0); q1 = q0;
+                if (g < G) {
+                    const int n0 = ws.site[g].ns - step * 32;
+                    if (lane < n0) {
+                        const int4 *rp = p.splits + 2 * (ws.site[g].soff + (long long)step * 32 + lane);
+                        q0 = ldg4(rp); q1 = ldg4(rp + 1);
+                        if (lane + 32 < n0) prefetch_l2(rp + 64);
+                    }
+                }
+            };
             for (int step = 0; step * 32 < nsmax; ++step) {
                 bool all_new = true;
+                int4 nq0, nq1;
+                load_split(step, 0, nq0, nq1);
+#pragma unroll 2
                 for (int g = 0; g < G; ++g) {
                     const SiteS &S = ws.site[g];
+                    const int4 q0 = nq0, q1 = nq1;
+                    load_split(step, g + 1, nq0, nq1);          /* next site's rows in flight */
                     const int n = min(32, S.ns - step * 32);
                     if (n <= 0) continue;
                     const bool rv = lane < n;
-                    int4 q0 = make_int4(0, 0, 0, 0), q1 = q0;
-                    if (rv) {
-                        const int4 *rp = p.splits + 2 * (S.soff + (long long)step * 32 + lane);
-                        q0 = ldg4(rp); q1 = ldg4(rp + 1);
-                    }
                     /* arrange breakends left to right, parsers.py:1143-1161 */
                     const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
                     const bool swap = (S.tA != S.tB) || (S.posA > S.posB);
