@@ -32,6 +32,12 @@
 
 namespace {
 
+#ifndef SVGT_ROWBUFS
+#define SVGT_ROWBUFS 2
+#endif
+#ifndef SVGT_SPLIT_PIPE
+#define SVGT_SPLIT_PIPE 0
+#endif
 constexpr int kWLibs = 4;           /* libraries with per-site windows cached in smem      */
 constexpr int kCoopWarps = SVGT_COOP_THREADS / 32;
 
@@ -563,6 +569,7 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     all_new = true;
                 }
             };
+#if SVGT_ROWBUFS == 3
             /* three row buffers in registers: two chunks are always in flight while one is scored */
             int cs[3] = {0, 0, 0}, cg[3] = {0, 0, 0};
             bool ok[3];
@@ -584,6 +591,23 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 if (ok[1]) load_rows(cs[1], cg[1], rl[1], rh[1]);
                 process(cs[2], cg[2], rl[2], rh[2], !ok[0] || cs[0] != cs[2]);
             }
+#else
+            /* two row buffers in registers: the next chunk is always in flight while one is scored */
+            int st0 = 0, g0 = 0;
+            int4 r0lo, r0hi, r1lo, r1hi;
+            bool more = advance(st0, g0);
+            if (more) load_rows(st0, g0, r0lo, r0hi);
+            while (more) {
+                int st1 = 0, g1 = 0;
+                const bool m1 = advance(st1, g1);
+                if (m1) load_rows(st1, g1, r1lo, r1hi);
+                process(st0, g0, r0lo, r0hi, !m1 || st1 != st0);
+                if (!m1) break;
+                more = advance(st0, g0);
+                if (more) load_rows(st0, g0, r0lo, r0hi);
+                process(st1, g1, r1lo, r1hi, !more || st0 != st1);
+            }
+#endif
             if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
             sum_frag = acc;
         }
@@ -607,13 +631,20 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
             };
             for (int step = 0; step * 32 < nsmax; ++step) {
                 bool all_new = true;
+#if SVGT_SPLIT_PIPE
                 int4 nq0, nq1;
                 load_split(step, 0, nq0, nq1);
 #pragma unroll 2
+#endif
                 for (int g = 0; g < G; ++g) {
                     const SiteS &S = ws.site[g];
+#if SVGT_SPLIT_PIPE
                     const int4 q0 = nq0, q1 = nq1;
                     load_split(step, g + 1, nq0, nq1);          /* next site's rows in flight */
+#else
+                    int4 q0, q1;
+                    load_split(step, g, q0, q1);
+#endif
                     const int n = min(32, S.ns - step * 32);
                     if (n <= 0) continue;
                     const bool rv = lane < n;

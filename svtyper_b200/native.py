@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsvgt.so")
+LIB_PATH = os.environ.get("SVGT_LIB") or os.path.join(HERE, "libsvgt.so")   # SVGT_LIB: A/B builds of the same ABI
 
 ABI_VERSION = 1
 OK, ERR_ARG, ERR_CUDA, ERR_LOG_TABLE, ERR_LIB_INDEX, ERR_NO_DEVICE, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6
