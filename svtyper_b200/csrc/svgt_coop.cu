@@ -33,10 +33,20 @@
 namespace {
 
 #ifndef SVGT_ROWBUFS
-#define SVGT_ROWBUFS 2
+#define SVGT_ROWBUFS 3
+#endif
+#ifndef SVGT_DIAG
+#define SVGT_DIAG 0          /* diagnostics only (wrong results), bit mask: 1 no scoring, 2 no phase B, 4 no split phase,
+                                8 no fragment-row loads, 16 no L2 prefetch */
 #endif
 #ifndef SVGT_SPLIT_PIPE
 #define SVGT_SPLIT_PIPE 0
+#endif
+#ifndef SVGT_USE_SAME
+#define SVGT_USE_SAME 1
+#endif
+#ifndef SVGT_L2_PREFETCH
+#define SVGT_L2_PREFETCH 0
 #endif
 constexpr int kWLibs = 4;           /* libraries with per-site windows cached in smem      */
 constexpr int kCoopWarps = SVGT_COOP_THREADS / 32;
@@ -133,7 +143,14 @@ __device__ __noinline__ void slow_row(const SvgtParams &p, const Tables &t, cons
 
 __device__ __forceinline__ bool in_win(int v, unsigned lo, unsigned w1) { return ((unsigned)v - lo) < w1; }
 
-__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void prefetch_l2(const void *ptr)
+{
+#if SVGT_L2_PREFETCH && !(SVGT_DIAG & 16)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;      /* measured: no effect once two chunks are in flight in registers (profiles/README.md) */
+#endif
+}
 
 
 /*
@@ -143,37 +160,67 @@ __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("pre
  * predicate.  All compares are exact for every int32 input (no subtract-and-test-sign tricks).
  */
 
-/* is_ref_seq for both reads against both breakends (parsers.py:801-816), both windows valid */
+/* is_ref_seq for both reads against both breakends (parsers.py:801-816), both windows valid.
+ * SAME: both breakends on one contig (tA == tB), so one tid compare serves both windows. */
+template <bool SAME>
 __device__ __forceinline__ void hits_chain(int a_start, int a_end, int b_start, int b_end, int tidA, int tidB, int fl,
                                            int tA, int tB, int wA0, int wA1, int wB0, int wB1, int &hitA, int &hitB)
 {
-    asm("{\n\t"
-        ".reg .pred p, q;\n\t"
-        ".reg .b32 t;\n\t"
-        "setp.le.s32 p, %2, %11;\n\t"
-        "setp.ge.and.s32 p, %3, %12, p;\n\t"
-        "setp.eq.and.s32 p, %6, %9, p;\n\t"
-        "setp.le.s32 q, %2, %13;\n\t"
-        "setp.ge.and.s32 q, %3, %14, q;\n\t"
-        "setp.eq.and.s32 q, %6, %10, q;\n\t"
-        "or.pred p, p, q;\n\t"
-        "and.b32 t, %8, 1;\n\t"
-        "setp.ne.and.s32 p, t, 0, p;\n\t"
-        "selp.s32 %0, 1, 0, p;\n\t"
-        "setp.le.s32 p, %4, %11;\n\t"
-        "setp.ge.and.s32 p, %5, %12, p;\n\t"
-        "setp.eq.and.s32 p, %7, %9, p;\n\t"
-        "setp.le.s32 q, %4, %13;\n\t"
-        "setp.ge.and.s32 q, %5, %14, q;\n\t"
-        "setp.eq.and.s32 q, %7, %10, q;\n\t"
-        "or.pred p, p, q;\n\t"
-        "and.b32 t, %8, 2;\n\t"
-        "setp.ne.and.s32 p, t, 0, p;\n\t"
-        "selp.s32 %1, 1, 0, p;\n\t"
-        "}"
-        : "=r"(hitA), "=r"(hitB)
-        : "r"(a_start), "r"(a_end), "r"(b_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(fl), "r"(tA), "r"(tB),
-          "r"(wA0), "r"(wA1), "r"(wB0), "r"(wB1));
+    if (SAME) {
+        asm("{\n\t"
+            ".reg .pred p, q;\n\t"
+            ".reg .b32 t;\n\t"
+            "setp.le.s32 p, %2, %11;\n\t"
+            "setp.ge.and.s32 p, %3, %12, p;\n\t"
+            "setp.le.s32 q, %2, %13;\n\t"
+            "setp.ge.and.s32 q, %3, %14, q;\n\t"
+            "or.pred p, p, q;\n\t"
+            "setp.eq.and.s32 p, %6, %9, p;\n\t"
+            "and.b32 t, %8, 1;\n\t"
+            "setp.ne.and.s32 p, t, 0, p;\n\t"
+            "selp.s32 %0, 1, 0, p;\n\t"
+            "setp.le.s32 p, %4, %11;\n\t"
+            "setp.ge.and.s32 p, %5, %12, p;\n\t"
+            "setp.le.s32 q, %4, %13;\n\t"
+            "setp.ge.and.s32 q, %5, %14, q;\n\t"
+            "or.pred p, p, q;\n\t"
+            "setp.eq.and.s32 p, %7, %9, p;\n\t"
+            "and.b32 t, %8, 2;\n\t"
+            "setp.ne.and.s32 p, t, 0, p;\n\t"
+            "selp.s32 %1, 1, 0, p;\n\t"
+            "}"
+            : "=r"(hitA), "=r"(hitB)
+            : "r"(a_start), "r"(a_end), "r"(b_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(fl), "r"(tA), "r"(tB),
+              "r"(wA0), "r"(wA1), "r"(wB0), "r"(wB1));
+    } else {
+        asm("{\n\t"
+            ".reg .pred p, q;\n\t"
+            ".reg .b32 t;\n\t"
+            "setp.le.s32 p, %2, %11;\n\t"
+            "setp.ge.and.s32 p, %3, %12, p;\n\t"
+            "setp.eq.and.s32 p, %6, %9, p;\n\t"
+            "setp.le.s32 q, %2, %13;\n\t"
+            "setp.ge.and.s32 q, %3, %14, q;\n\t"
+            "setp.eq.and.s32 q, %6, %10, q;\n\t"
+            "or.pred p, p, q;\n\t"
+            "and.b32 t, %8, 1;\n\t"
+            "setp.ne.and.s32 p, t, 0, p;\n\t"
+            "selp.s32 %0, 1, 0, p;\n\t"
+            "setp.le.s32 p, %4, %11;\n\t"
+            "setp.ge.and.s32 p, %5, %12, p;\n\t"
+            "setp.eq.and.s32 p, %7, %9, p;\n\t"
+            "setp.le.s32 q, %4, %13;\n\t"
+            "setp.ge.and.s32 q, %5, %14, q;\n\t"
+            "setp.eq.and.s32 q, %7, %10, q;\n\t"
+            "or.pred p, p, q;\n\t"
+            "and.b32 t, %8, 2;\n\t"
+            "setp.ne.and.s32 p, t, 0, p;\n\t"
+            "selp.s32 %1, 1, 0, p;\n\t"
+            "}"
+            : "=r"(hitA), "=r"(hitB)
+            : "r"(a_start), "r"(a_end), "r"(b_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(fl), "r"(tA), "r"(tB),
+              "r"(wA0), "r"(wA1), "r"(wB0), "r"(wB1));
+    }
 }
 
 /*
@@ -184,78 +231,105 @@ __device__ __forceinline__ void hits_chain(int a_start, int a_end, int b_start, 
  *     p_ref = (refA | refB) & (!(refA & refB) | DEL) & p_conc ? pmA * pmB * (refA + refB) / 2 : 0   :336-350
  * Outputs LUT indices (0 selects pm[0] == 0.0; +256 selects the halved table) and a `tie` flag
  * (19*h1 == h2 != 0: the caller evaluates the literal fp64 expression).
+ * SAME: tA == tB, so "both reads on the site's contig" is one predicate shared by all three tests.
  */
+#define SVGT_PE_DECL                                                                                  \
+    "{\n\t"                                                                                           \
+    ".reg .pred pf, pa, pfr, ra, rb, p1, p2, pc, pt, pboth, pany, pdel, pron, paon;\n\t"             \
+    ".reg .b32 d, o, k2, h1, h2, l19, t;\n\t"                                                         \
+    ".reg .b64 ad;\n\t"                                                                               \
+    "setp.ne.s32 pf, %10, 0;\n\t"
+#define SVGT_PE_TESTS_ANY                                                                             \
+    "setp.eq.and.s32 pa, %7, %11, pf;\n\t"                                                            \
+    "setp.eq.and.s32 pa, %8, %12, pa;\n\t"                                                            \
+    "setp.eq.and.s32 pa, %9, %13, pa;\n\t"                                                            \
+    "sub.s32 d, %5, %15;\n\t"                                                                         \
+    "setp.lt.and.u32 pa, d, %16, pa;\n\t"                                                             \
+    "sub.s32 d, %6, %17;\n\t"                                                                         \
+    "setp.lt.and.u32 pa, d, %18, pa;\n\t"                                                             \
+    "setp.eq.and.s32 pfr, %9, 2, pf;\n\t"                                                             \
+    "setp.eq.and.s32 ra, %7, %11, pfr;\n\t"                                                           \
+    "setp.eq.and.s32 ra, %8, %11, ra;\n\t"                                                            \
+    "sub.s32 d, %5, %19;\n\t"                                                                         \
+    "setp.lt.and.u32 ra, d, %20, ra;\n\t"                                                             \
+    "sub.s32 d, %6, %21;\n\t"                                                                         \
+    "setp.lt.and.u32 ra, d, %22, ra;\n\t"                                                             \
+    "setp.eq.and.s32 rb, %7, %12, pfr;\n\t"                                                           \
+    "setp.eq.and.s32 rb, %8, %12, rb;\n\t"                                                            \
+    "sub.s32 d, %5, %23;\n\t"                                                                         \
+    "setp.lt.and.u32 rb, d, %24, rb;\n\t"                                                             \
+    "sub.s32 d, %6, %25;\n\t"                                                                         \
+    "setp.lt.and.u32 rb, d, %26, rb;\n\t"
+#define SVGT_PE_TESTS_SAME                                                                            \
+    "setp.eq.and.s32 pf, %7, %11, pf;\n\t"                                                            \
+    "setp.eq.and.s32 pf, %8, %11, pf;\n\t"                                                            \
+    "setp.eq.and.s32 pa, %9, %13, pf;\n\t"                                                            \
+    "sub.s32 d, %5, %15;\n\t"                                                                         \
+    "setp.lt.and.u32 pa, d, %16, pa;\n\t"                                                             \
+    "sub.s32 d, %6, %17;\n\t"                                                                         \
+    "setp.lt.and.u32 pa, d, %18, pa;\n\t"                                                             \
+    "setp.eq.and.s32 pfr, %9, 2, pf;\n\t"                                                             \
+    "sub.s32 d, %5, %19;\n\t"                                                                         \
+    "setp.lt.and.u32 ra, d, %20, pfr;\n\t"                                                            \
+    "sub.s32 d, %6, %21;\n\t"                                                                         \
+    "setp.lt.and.u32 ra, d, %22, ra;\n\t"                                                             \
+    "sub.s32 d, %5, %23;\n\t"                                                                         \
+    "setp.lt.and.u32 rb, d, %24, pfr;\n\t"                                                            \
+    "sub.s32 d, %6, %25;\n\t"                                                                         \
+    "setp.lt.and.u32 rb, d, %26, rb;\n\t"
+/* with SAME, pf has been narrowed to "fast and both reads on the contig": a pair elsewhere can
+ * not straddle anything, so skipping its histogram look-ups changes nothing */
+#define SVGT_PE_PCONC                                                                                 \
+    "sad.s32 o, %6, %5, 0;\n\t"                                                                       \
+    "sub.s32 k2, o, %27;\n\t"                                                                         \
+    "mov.b32 h1, 0;\n\t"                                                                              \
+    "mov.b32 h2, 0;\n\t"                                                                              \
+    "setp.lt.and.u32 p1, o, %29, pf;\n\t"                                                             \
+    "setp.lt.and.u32 p2, k2, %29, pf;\n\t"                                                            \
+    "add.s32 t, o, %28;\n\t"                                                                          \
+    "mad.wide.u32 ad, t, 4, %30;\n\t"                                                                 \
+    "@p1 ld.u32 h1, [ad];\n\t"                                                                        \
+    "add.s32 t, k2, %28;\n\t"                                                                         \
+    "mad.wide.u32 ad, t, 4, %30;\n\t"                                                                 \
+    "@p2 ld.u32 h2, [ad];\n\t"                                                                        \
+    "mul.lo.u32 l19, h1, 19;\n\t"                                                                     \
+    "setp.gt.u32 pc, l19, h2;\n\t"                                                                    \
+    "setp.eq.u32 pt, l19, h2;\n\t"                                                                    \
+    "setp.ne.and.u32 pt, h2, 0, pt;\n\t"                                                              \
+    "selp.s32 %3, 1, 0, pt;\n\t"
+#define SVGT_PE_WEIGHTS                                                                               \
+    "setp.ne.s32 pdel, %14, 0;\n\t"                                                                   \
+    "and.pred pboth, ra, rb;\n\t"                                                                     \
+    "or.pred pany, ra, rb;\n\t"                                                                       \
+    "and.pred p1, pboth, !pdel;\n\t"                                                                  \
+    "and.pred pron, pany, !p1;\n\t"                                                                   \
+    "and.pred pron, pron, pc;\n\t"                                                                    \
+    "and.pred p2, pdel, pc;\n\t"                                                                      \
+    "and.pred paon, pa, !p2;\n\t"                                                                     \
+    "selp.s32 %0, %31, 0, paon;\n\t"                                                                  \
+    "selp.s32 %1, %31, 0, pron;\n\t"                                                                  \
+    "add.s32 t, %32, 256;\n\t"                                                                        \
+    "selp.s32 %2, %32, t, pboth;\n\t"                                                                 \
+    "selp.s32 %4, 1, 0, pa;\n\t"                                                                      \
+    "}"
+#define SVGT_PE_OPERANDS                                                                              \
+    : "=r"(idx_alt), "=r"(idx_ref), "=r"(idx_refB), "=r"(tie), "=r"(alt_out)                           \
+    : "r"(a_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(st), "r"(fastflag), "r"(tA), "r"(tB), "r"(o12),  \
+      "r"(is_del), "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w2.x), "r"(w2.y), "r"(w2.z), "r"(w2.w), \
+      "r"(w3.x), "r"(w3.y), "r"(w3.z), "r"(w3.w), "r"(Lk), "r"(hist_off), "r"(hist_len), "l"(hist), "r"(mqA), \
+      "r"(mqB)
+
+template <bool SAME>
 __device__ __forceinline__ void pe_chain(int a_start, int b_end, int tidA, int tidB, int st, int fastflag,
                                          int tA, int tB, int o12, int is_del, uint4 w0, uint4 w2, uint4 w3,
                                          unsigned Lk, unsigned hist_off, unsigned hist_len, const unsigned *hist,
                                          int mqA, int mqB, int &idx_alt, int &idx_ref, int &idx_refB, int &tie,
                                          int &alt_out)
 {
-    asm("{\n\t"
-        ".reg .pred pf, pa, pfr, ra, rb, p1, p2, pc, pt, pboth, pany, pdel, pron, paon;\n\t"
-        ".reg .b32 d, o, k2, h1, h2, l19, t;\n\t"
-        ".reg .b64 ad;\n\t"
-        "setp.ne.s32 pf, %10, 0;\n\t"
-        /* alt: tids (A on A, B on B), strands, both windows */
-        "setp.eq.and.s32 pa, %7, %11, pf;\n\t"
-        "setp.eq.and.s32 pa, %8, %12, pa;\n\t"
-        "setp.eq.and.s32 pa, %9, %13, pa;\n\t"
-        "sub.s32 d, %5, %15;\n\t"
-        "setp.lt.and.u32 pa, d, %16, pa;\n\t"
-        "sub.s32 d, %6, %17;\n\t"
-        "setp.lt.and.u32 pa, d, %18, pa;\n\t"
-        /* reference-spanning pairs are forward/reverse (st == 2) */
-        "setp.eq.and.s32 pfr, %9, 2, pf;\n\t"
-        "setp.eq.and.s32 ra, %7, %11, pfr;\n\t"
-        "setp.eq.and.s32 ra, %8, %11, ra;\n\t"
-        "sub.s32 d, %5, %19;\n\t"
-        "setp.lt.and.u32 ra, d, %20, ra;\n\t"
-        "sub.s32 d, %6, %21;\n\t"
-        "setp.lt.and.u32 ra, d, %22, ra;\n\t"
-        "setp.eq.and.s32 rb, %7, %12, pfr;\n\t"
-        "setp.eq.and.s32 rb, %8, %12, rb;\n\t"
-        "sub.s32 d, %5, %23;\n\t"
-        "setp.lt.and.u32 rb, d, %24, rb;\n\t"
-        "sub.s32 d, %6, %25;\n\t"
-        "setp.lt.and.u32 rb, d, %26, rb;\n\t"
-        /* p_concordant on counts: h1 = hist[o], h2 = hist[o - Lk] (missing keys are 0) */
-        "sad.s32 o, %6, %5, 0;\n\t"
-        "sub.s32 k2, o, %27;\n\t"
-        "mov.b32 h1, 0;\n\t"
-        "mov.b32 h2, 0;\n\t"
-        "setp.lt.and.u32 p1, o, %29, pf;\n\t"
-        "setp.lt.and.u32 p2, k2, %29, pf;\n\t"
-        "add.s32 t, o, %28;\n\t"
-        "mad.wide.u32 ad, t, 4, %30;\n\t"
-        "@p1 ld.u32 h1, [ad];\n\t"
-        "add.s32 t, k2, %28;\n\t"
-        "mad.wide.u32 ad, t, 4, %30;\n\t"
-        "@p2 ld.u32 h2, [ad];\n\t"
-        "mul.lo.u32 l19, h1, 19;\n\t"
-        "setp.gt.u32 pc, l19, h2;\n\t"
-        "setp.eq.u32 pt, l19, h2;\n\t"
-        "setp.ne.and.u32 pt, h2, 0, pt;\n\t"
-        "selp.s32 %3, 1, 0, pt;\n\t"
-        /* weights */
-        "setp.ne.s32 pdel, %14, 0;\n\t"
-        "and.pred pboth, ra, rb;\n\t"
-        "or.pred pany, ra, rb;\n\t"
-        "and.pred p1, pboth, !pdel;\n\t"         /* both sides straddled on a non-DEL: no ref evidence */
-        "and.pred pron, pany, !p1;\n\t"
-        "and.pred pron, pron, pc;\n\t"
-        "and.pred p2, pdel, pc;\n\t"
-        "and.pred paon, pa, !p2;\n\t"
-        "selp.s32 %0, %31, 0, paon;\n\t"
-        "selp.s32 %1, %31, 0, pron;\n\t"
-        "add.s32 t, %32, 256;\n\t"
-        "selp.s32 %2, %32, t, pboth;\n\t"
-        "selp.s32 %4, 1, 0, pa;\n\t"
-        "}"
-        : "=r"(idx_alt), "=r"(idx_ref), "=r"(idx_refB), "=r"(tie), "=r"(alt_out)
-        : "r"(a_start), "r"(b_end), "r"(tidA), "r"(tidB), "r"(st), "r"(fastflag), "r"(tA), "r"(tB), "r"(o12),
-          "r"(is_del), "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w2.x), "r"(w2.y), "r"(w2.z), "r"(w2.w),
-          "r"(w3.x), "r"(w3.y), "r"(w3.z), "r"(w3.w), "r"(Lk), "r"(hist_off), "r"(hist_len), "l"(hist), "r"(mqA),
-          "r"(mqB));
+    if (SAME)
+        asm(SVGT_PE_DECL SVGT_PE_TESTS_SAME SVGT_PE_PCONC SVGT_PE_WEIGHTS SVGT_PE_OPERANDS);
+    else
+        asm(SVGT_PE_DECL SVGT_PE_TESTS_ANY SVGT_PE_PCONC SVGT_PE_WEIGHTS SVGT_PE_OPERANDS);
 }
 
 /* ordered replay of one chain over `cnt` parked rows (phase B).
@@ -380,12 +454,17 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
             __syncwarp();
         }
 
-        /* pull the first 1 KB of every site's fragment and split rows towards L2 now; later steps
-         * prefetch one super-step (G chunks) ahead of the register loads */
+        /* pull the first 1 KB of every site's fragment and split rows towards L2 now (lane g, one
+         * 128-byte line per instruction); later steps prefetch one super-step ahead of the loads */
+        if (lane < G) {
+            const SiteS &S = ws.site[lane];
+            const char *fp = reinterpret_cast<const char *>(p.frags + 2 * S.foff);
+            const char *sp = reinterpret_cast<const char *>(p.splits + 2 * S.soff);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            if (lane < ws.site[g].nf) prefetch_l2(p.frags + 2 * (ws.site[g].foff + lane));
-            if (lane < ws.site[g].ns) prefetch_l2(p.splits + 2 * (ws.site[g].soff + lane));
+            for (int k = 0; k < 8; ++k) {
+                if (k * 4 < S.nf) prefetch_l2(fp + k * 128);
+                if (k * 4 < S.ns) prefetch_l2(sp + k * 128);
+            }
         }
 
         double sum_frag = 0.0;      /* lane 4g+c: chain c of the fragment rows of site g */
@@ -417,7 +496,12 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 lo = make_int4(0, 0, 0, 0); hi = lo;
                 if (lane < n) {
                     const int4 *rp = p.frags + 2 * (ws.site[g].foff + (long long)st * 32 + lane);
+#if SVGT_DIAG & 8
+                    lo = make_int4(lane * st, g, n, lane + 100); hi = make_int4(0, 0, 60 | (60 << 8), 0x1b);
+                    (void)rp;
+#else
                     lo = ldg4(rp); hi = ldg4(rp + 1);
+#endif
                 }
             };
             /* score one 32-row chunk (phase A); `flush` = last chunk of its super-step (phase B follows) */
@@ -452,8 +536,14 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
 
                 /* ---- is_ref_seq hits (parsers.py:801-816) ---- */
                 int hitA, hitB;
-                if (common) {
-                    hits_chain(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, fl, s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, hitA, hitB);
+                const bool same = SVGT_USE_SAME && s0.x == s0.y;    /* both breakends on one contig */
+#if SVGT_DIAG & 1
+                hitA = lo.x & 1; hitB = lo.w & 1;
+#else
+                if (common && same) {
+                    hits_chain<true>(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, fl, s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, hitA, hitB);
+                } else if (common) {
+                    hits_chain<false>(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, fl, s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, hitA, hitB);
                 } else {
                     const bool okA = (smeta >> 8) & 1, okB = (smeta >> 9) & 1;
                     const bool ea = hi.x == s0.x, eb = hi.x == s0.y, fa = hi.y == s0.x, fb = hi.y == s0.y;
@@ -462,6 +552,7 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     hitB = ((fl & F_HAS_B) != 0) && ((fa && okA && lo.z <= s0.z && lo.w >= s0.w) ||
                                                      (fb && okB && lo.z <= s1.x && lo.w >= s1.y));
                 }
+#endif
                 /* EXTRA interval rows feed the next main row's MULTI slots (evidence.py) */
                 const unsigned XM = __ballot_sync(full, (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B | F_CONT)) != 0);
                 unsigned nm = vm;
@@ -509,10 +600,19 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     ia = alt_on ? mqA : 0; ir = ref_on ? mqA : 0; irB = mqB + (both ? 0 : 256);
                 };
                 int idx_alt, idx_ref, idx_refB, tie = 0;
-                if (common) {
+#if SVGT_DIAG & 1
+                idx_alt = mqA & st; idx_ref = mqB & o12; idx_refB = mqB;
+                if (false) {
+#else
+                if (common && same) {
+#endif
                     int alt_i;
-                    pe_chain(lo.x, lo.w, hi.x, hi.y, st, (int)fast, s0.x, s0.y, o12, (int)is_del, w0, w2, w3, w4.x, w4.y,
-                             w4.z, hist, mqA, mqB, idx_alt, idx_ref, idx_refB, tie, alt_i);
+                    pe_chain<true>(lo.x, lo.w, hi.x, hi.y, st, (int)fast, s0.x, s0.y, o12, (int)is_del, w0, w2, w3, w4.x,
+                                   w4.y, w4.z, hist, mqA, mqB, idx_alt, idx_ref, idx_refB, tie, alt_i);
+                } else if (common) {
+                    int alt_i;
+                    pe_chain<false>(lo.x, lo.w, hi.x, hi.y, st, (int)fast, s0.x, s0.y, o12, (int)is_del, w0, w2, w3, w4.x,
+                                    w4.y, w4.z, hist, mqA, mqB, idx_alt, idx_ref, idx_refB, tie, alt_i);
                 } else {
                     const bool ea = hi.x == s0.x, eb = hi.x == s0.y, fa = hi.y == s0.x, fb = hi.y == s0.y;
                     const bool ab = ea & fb & fast;
@@ -563,33 +663,31 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                         const double *row0 = &ws.contrib[gb][0][0];
                         const double *px = row0 + (c == 0 ? 0 : c + 1);
                         const double *py = (c == 0) ? row0 + 1 : ws.zero;
+#if !(SVGT_DIAG & 2)
                         replay_chain<ASSOC>(px, py, c == 0 ? 4 : 0, cnt, ws.newmask[gb], all_new, acc, pend);
+#else
+                        acc += px[0] + py[0] + cnt;
+#endif
                     }
                     __syncwarp();
                     all_new = true;
                 }
             };
 #if SVGT_ROWBUFS == 3
-            /* three row buffers in registers: two chunks are always in flight while one is scored */
-            int cs[3] = {0, 0, 0}, cg[3] = {0, 0, 0};
-            bool ok[3];
-            int4 rl[3], rh[3];
-            ok[0] = advance(cs[0], cg[0]);
-            if (ok[0]) load_rows(cs[0], cg[0], rl[0], rh[0]);
-            ok[1] = ok[0] && advance(cs[1], cg[1]);
-            if (ok[1]) load_rows(cs[1], cg[1], rl[1], rh[1]);
-            while (ok[0]) {
-                ok[2] = ok[1] && advance(cs[2], cg[2]);
-                if (ok[2]) load_rows(cs[2], cg[2], rl[2], rh[2]);
-                process(cs[0], cg[0], rl[0], rh[0], !ok[1] || cs[1] != cs[0]);
-                if (!ok[1]) break;
-                ok[0] = ok[2] && advance(cs[0], cg[0]);
-                if (ok[0]) load_rows(cs[0], cg[0], rl[0], rh[0]);
-                process(cs[1], cg[1], rl[1], rh[1], !ok[2] || cs[2] != cs[1]);
-                if (!ok[2]) break;
-                ok[1] = ok[0] && advance(cs[1], cg[1]);
-                if (ok[1]) load_rows(cs[1], cg[1], rl[1], rh[1]);
-                process(cs[2], cg[2], rl[2], rh[2], !ok[0] || cs[0] != cs[2]);
+            /* rotating register queue: while one chunk is scored the next TWO are in flight; the
+             * rotation is 16 register moves (FMA pipe, otherwise idle) instead of a third code copy */
+            int cs0 = 0, cg0 = 0, cs1 = 0, cg1 = 0, cs2 = 0, cg2 = 0;
+            int4 l0, h0, l1, h1, l2, h2;
+            bool k0 = advance(cs0, cg0);
+            if (k0) load_rows(cs0, cg0, l0, h0);
+            bool k1 = k0 && advance(cs1, cg1);
+            if (k1) load_rows(cs1, cg1, l1, h1);
+            while (k0) {
+                const bool k2 = k1 && advance(cs2, cg2);
+                if (k2) load_rows(cs2, cg2, l2, h2);
+                process(cs0, cg0, l0, h0, !k1 || cs1 != cs0);
+                cs0 = cs1; cg0 = cg1; l0 = l1; h0 = h1; k0 = k1;
+                cs1 = cs2; cg1 = cg2; l1 = l2; h1 = h2; k1 = k2;
             }
 #else
             /* two row buffers in registers: the next chunk is always in flight while one is scored */
@@ -614,39 +712,44 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
 
         /* ================= split rows ================= */
         {
-            int nsmax = 0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) nsmax = max(nsmax, ws.site[g].ns);
             double acc = 0.0, pend = 0.0;
+            const int my_ns = lane < G ? ws.site[lane].ns : 0;
+            int sp_step = -1;
+            unsigned sp_mask = 0u;
+            auto advance_split = [&](int &st, int &g) -> bool {
+                if (sp_mask == 0u) {
+                    ++sp_step;
+                    sp_mask = __ballot_sync(full, my_ns > sp_step * 32);
+                    if (sp_mask == 0u || (SVGT_DIAG & 4)) return false;
+                }
+                g = __ffs(sp_mask) - 1;
+                sp_mask &= sp_mask - 1u;
+                st = sp_step;
+                return true;
+            };
             auto load_split = [&](int step, int g, int4 &q0, int4 &q1) {
                 q0 = make_int4(0, 0, 0, 0); q1 = q0;
-                if (g < G) {
-                    const int n0 = ws.site[g].ns - step * 32;
-                    if (lane < n0) {
-                        const int4 *rp = p.splits + 2 * (ws.site[g].soff + (long long)step * 32 + lane);
-                        q0 = ldg4(rp); q1 = ldg4(rp + 1);
-                        if (lane + 32 < n0) prefetch_l2(rp + 64);
-                    }
+                const int n0 = ws.site[g].ns - step * 32;
+                if (lane < n0) {
+                    const int4 *rp = p.splits + 2 * (ws.site[g].soff + (long long)step * 32 + lane);
+                    q0 = ldg4(rp); q1 = ldg4(rp + 1);
                 }
             };
-            for (int step = 0; step * 32 < nsmax; ++step) {
-                bool all_new = true;
-#if SVGT_SPLIT_PIPE
-                int4 nq0, nq1;
-                load_split(step, 0, nq0, nq1);
-#pragma unroll 2
-#endif
-                for (int g = 0; g < G; ++g) {
+            bool all_new = true;
+            int ss0 = 0, sg0 = 0, ss1 = 0, sg1 = 0, ss2 = 0, sg2 = 0;
+            int4 a0, b0, a1, b1, a2, b2;
+            bool e0 = advance_split(ss0, sg0);
+            if (e0) load_split(ss0, sg0, a0, b0);
+            bool e1 = e0 && advance_split(ss1, sg1);
+            if (e1) load_split(ss1, sg1, a1, b1);
+            while (e0) {
+                const bool e2 = e1 && advance_split(ss2, sg2);
+                if (e2) load_split(ss2, sg2, a2, b2);          /* two chunks in flight while one is scored */
+                {
+                    const int step = ss0, g = sg0;
+                    const int4 q0 = a0, q1 = b0;
                     const SiteS &S = ws.site[g];
-#if SVGT_SPLIT_PIPE
-                    const int4 q0 = nq0, q1 = nq1;
-                    load_split(step, g + 1, nq0, nq1);          /* next site's rows in flight */
-#else
-                    int4 q0, q1;
-                    load_split(step, g, q0, q1);
-#endif
                     const int n = min(32, S.ns - step * 32);
-                    if (n <= 0) continue;
                     const bool rv = lane < n;
                     /* arrange breakends left to right, parsers.py:1143-1161 */
                     const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
@@ -677,14 +780,19 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     *dst = make_double2(soft ? 0.0 : p_alt, soft ? p_alt : 0.0);
                     if (lane == 0) ws.newmask[g] = nm;
                 }
-                __syncwarp();
-                if (gb < G && c < 2) {
-                    int cnt = ws.site[gb].ns - step * 32;
-                    cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
-                    const double *px = &ws.contrib[gb][0][0] + c;
-                    replay_chain<ASSOC>(px, ws.zero, 0, cnt, ws.newmask[gb], all_new, acc, pend);
+                if (!e1 || ss1 != ss0) {                        /* last chunk of its super-step: phase B */
+                    __syncwarp();
+                    if (gb < G && c < 2) {
+                        int cnt = ws.site[gb].ns - ss0 * 32;
+                        cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+                        const double *px = &ws.contrib[gb][0][0] + c;
+                        replay_chain<ASSOC>(px, ws.zero, 0, cnt, ws.newmask[gb], all_new, acc, pend);
+                    }
+                    __syncwarp();
+                    all_new = true;
                 }
-                __syncwarp();
+                ss0 = ss1; sg0 = sg1; a0 = a1; b0 = b1; e0 = e1;
+                ss1 = ss2; sg1 = sg2; a1 = a2; b1 = b2; e1 = e2;
             }
             if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
             sum_split = acc;

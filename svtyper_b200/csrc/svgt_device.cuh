@@ -62,7 +62,22 @@ struct Acc {
     int err;
 };
 
-__device__ __forceinline__ int4 ldg4(const int4 *p) { return __ldg(p); }
+#ifndef SVGT_LDG_MODE
+#define SVGT_LDG_MODE 2
+#endif
+/* 128-bit row load: 0 = read-only (nc) path, 1 = L2 only (.cg), 2 = streaming (.cs), 3 = plain */
+__device__ __forceinline__ int4 ldg4(const int4 *p)
+{
+#if SVGT_LDG_MODE == 1
+    return __ldcg(p);
+#elif SVGT_LDG_MODE == 2
+    return __ldcs(p);
+#elif SVGT_LDG_MODE == 3
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
 
 __device__ __forceinline__ LibK derive_lib(const SvgtParams &p, int l, int *err)
 {

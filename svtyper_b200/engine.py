@@ -146,21 +146,22 @@ class Engine(object):
         dev.status = torch.zeros(4, dtype=torch.int32, device=self.device)
         return dev
 
-    def score(self, dev, stream=None):
+    def score(self, dev, stream=None, out=None):
         """Asynchronously score a DeviceBatch on `stream` (default: torch's current stream).
 
-        Returns dev.out (uint8 [n_sites, 80] device tensor).  Call `check(dev)` after a
-        synchronisation to surface per-site error flags.
+        Returns the output tensor (`out` or dev.out: uint8 [n_sites, 80] on the device).  Call
+        `check(dev)` after a synchronisation to surface per-site error flags.
         """
         torch = _torch()
         s = torch.cuda.current_stream(self.device) if stream is None else stream
+        out = dev.out if out is None else out
         with torch.cuda.device(self.device):
-            rc = self._lib.svgt_score_batch(ctypes.byref(dev.desc), ctypes.c_void_p(dev.out.data_ptr()),
+            rc = self._lib.svgt_score_batch(ctypes.byref(dev.desc), ctypes.c_void_p(out.data_ptr()),
                                             ctypes.c_void_p(dev.status.data_ptr()),
                                             ctypes.c_void_p(s.cuda_stream))
         native.check(rc)
         self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(dev.desc))
-        return dev.out
+        return out
 
     def check(self, dev):
         st = dev.status.cpu().numpy()
