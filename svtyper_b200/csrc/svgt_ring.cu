@@ -1,0 +1,372 @@
+/*
+ * svgt_ring.cu -- warp-cooperative tally kernel with TMA-staged rows (variant 4).
+ *
+ * Same two-phase mapping as svgt_coop.cu (phase A: one evidence row per lane; phase B: one ordered
+ * fp64 chain per lane, singlesample.py:355-404), but the rows do not travel through registers:
+ *
+ *   - every 32-row chunk of a site (fragment rows first, then split rows: both are 32-byte rows,
+ *     so one stream) is ONE cp.async.bulk (TMA 1-D, UBLKCP) of <= 1 KB from HBM into a slot of a
+ *     per-warp shared-memory ring, completing on that slot's mbarrier.  The producer side is just
+ *     the same warp running up to RS - 4 chunks ahead; completion is tracked by mbarrier phases,
+ *     not by register scoreboards, so the copies really are in flight while earlier chunks are
+ *     scored (register prefetch deeper than one chunk did not overlap: svgt_coop.cu, profiles/).
+ *   - phase A scores a slot IN PLACE: lane l reads its 32-byte row and overwrites it with the
+ *     32 bytes it parks for phase B {a + b, LUT indices of a and b, p_ref, p_alt}.
+ *   - phase B runs after every group of <= 4 chunks of one super-step: lane 4g+c replays chain c
+ *     of site g straight out of the ring slot; the slot is then free for the producer again.
+ *
+ * The genotype call is the same second launch (svgt_call_kernel in svgt_coop.cu).
+ */
+#include "svgt_coop.cuh"
+
+namespace {
+
+constexpr int RG = 8;               /* sites per work unit                                        */
+constexpr int RS = 8;               /* ring slots per warp                                         */
+constexpr int kGroup = 4;           /* chunks per phase-B group (RS - kGroup chunks stay in flight) */
+constexpr int kRingSlotBytes = 33 * 32; /* 32 rows + 32 B pad: chain lanes of different sites hit distinct banks */
+
+struct alignas(128) RingSmem {
+    SiteS site[RG];
+    Win win[RG][kWLibs];
+    unsigned char slot[RS][kRingSlotBytes];
+    unsigned long long bar[RS];
+    double zero[2];
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+/* warp-uniform cursor over a unit's chunk stream: fragment chunks step-major, then split chunks */
+struct Cursor {
+    int phase, step;
+    unsigned mask;
+};
+
+template <int ASSOC>
+__global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const SvgtParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_pm = reinterpret_cast<double *>(smem_raw);
+    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 512);     /* pm[0..255], then pm[q] / 2 */
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
+    off = (off + 127) & ~(size_t)127;
+    RingSmem *s_warp = reinterpret_cast<RingSmem *>(smem_raw + off);
+    off += sizeof(RingSmem) * kCoopWarps;
+    unsigned *s_hist = reinterpret_cast<unsigned *>(smem_raw + off);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    int err = 0;
+    const int nl = p.n_lib < SVGT_SMEM_LIBS ? p.n_lib : SVGT_SMEM_LIBS;
+    for (int i = tid; i < 256; i += SVGT_COOP_THREADS) {
+        const double v = p.pm[i];
+        s_pm[i] = v;
+        s_pm[256 + i] = __dmul_rn(v, 0.5);
+    }
+    for (int i = tid; i < nl; i += SVGT_COOP_THREADS) s_lib[i] = derive_lib(p, i, &err);
+    int big = 0;
+    for (long long i = tid; i < p.n_hist; i += SVGT_COOP_THREADS) {
+        const unsigned v = p.hist[i];
+        if (p.hist_in_smem) s_hist[i] = v;
+        big |= v >= (1u << 26);
+    }
+    RingSmem &ws = s_warp[warp];
+    if (lane < 2) ws.zero[lane] = 0.0;
+    if (lane < RS) mbar_init(&ws.bar[lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const bool small_counts = __syncthreads_or(big) == 0;
+
+    Tables t;
+    t.pm = s_pm; t.libs = s_lib; t.hist = p.hist_in_smem ? s_hist : p.hist;
+    t.conc = p.consts[C_CONC]; t.disc = p.consts[C_DISC];
+    const unsigned *hist = t.hist;
+    const int m = p.min_aligned, slop = p.split_slop;
+
+    const int gb = lane >> 2, c = lane & 3;                /* phase-B role: chain c of site gb */
+    const long long n_units = (p.n_sites + RG - 1) / RG;
+    unsigned q_issue = 0, q_cons = 0, q_done = 0;           /* running chunk counters of this warp */
+
+    for (;;) {
+        long long unit = 0;
+        if (lane == 0) unit = (long long)atomicAdd(reinterpret_cast<unsigned *>(p.status + 1), 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= n_units) break;
+
+        /* ---- lanes 0..RG-1 read their site row and publish the scalars ---- */
+        int my_nf = 0, my_ns = 0;
+        {
+            const long long idx = unit * RG + lane;
+            const bool valid = lane < RG && idx < p.n_sites;
+            long long site = 0;
+            if (valid) site = p.order ? (long long)p.order[idx] : idx;
+            int4 a = make_int4(0, 0, 0, 0), b = a, cc = a, d = a;
+            if (valid) {
+                const int4 *sp = p.sites + site * 4;
+                a = ldg4(sp); b = ldg4(sp + 1); cc = ldg4(sp + 2); d = ldg4(sp + 3);
+            }
+            const int meta = cc.y;
+            const bool ranged = site_fields_in_range(a, b, m, slop);
+            const bool run = valid && !(meta & SITE_SKIP) && ranged;
+            const long long foff = ((long long)(unsigned)cc.z) | ((long long)cc.w << 32);
+            const long long soff = ((long long)(unsigned)d.y) | ((long long)d.z << 32);
+            int nf = run ? d.x : 0, ns = run ? d.w : 0;
+            if (nf < 0 || foff < 0 || foff + nf > p.n_frag) { nf = 0; err = SVGT_ERR_ARG; }
+            if (ns < 0 || soff < 0 || soff + ns > p.n_split) { ns = 0; err = SVGT_ERR_ARG; }
+            my_nf = nf; my_ns = ns;
+            if (lane < RG) {
+                SiteS &S = ws.site[lane];
+                S.tA = b.z; S.tB = b.w;
+                S.wA0 = a.x - m; S.wA1 = a.x + m; S.wB0 = a.y - m; S.wB1 = a.y + m;
+                S.meta = (meta & 15) | ((a.x - m >= 0) << 8) | ((a.y - m >= 0) << 9);
+                S.var_length = cc.x;
+                S.posA = a.x; S.posB = a.y; S.ciA0 = a.z; S.ciA1 = a.w; S.ciB0 = b.x; S.ciB1 = b.y;
+                S.dAB = a.y - a.x; S.nf = nf; S.foff = foff; S.soff = soff; S.ns = ns;
+                S.slot = valid ? 1 : 0;
+            }
+            __syncwarp();
+            for (int i = lane; i < RG * kWLibs; i += 32) {
+                const int g = i / kWLibs, l = i % kWLibs;
+                if (l < nl) { if (ws.site[g].nf) ws.win[g][l] = make_win(ws.site[g], s_lib[l], m, small_counts); }
+                else ws.win[g][l].flags = 0u;
+            }
+            __syncwarp();
+        }
+
+        /* ---- the unit's chunk stream: two cursors over the same sequence ---- */
+        auto next_chunk = [&](Cursor &cu, int &phase, int &step, int &g) -> bool {
+            for (;;) {
+                if (cu.mask) {
+                    g = __ffs(cu.mask) - 1;
+                    cu.mask &= cu.mask - 1u;
+                    phase = cu.phase; step = cu.step;
+                    return true;
+                }
+                ++cu.step;
+                const unsigned mk = __ballot_sync(full, (cu.phase == 0 ? my_nf : my_ns) > cu.step * 32);
+                if (mk) { cu.mask = mk; continue; }
+                if (cu.phase == 0) { cu.phase = 1; cu.step = -1; continue; }
+                return false;
+            }
+        };
+        Cursor prod = {0, -1, 0u}, cons = {0, -1, 0u};
+        bool prod_more = true;
+        auto produce = [&]() {
+            /* issue bulk copies while a slot is free (chunks q_done .. q_issue-1 occupy slots) */
+            while (prod_more && (q_issue - q_done) < (unsigned)RS) {
+                int ph, st, g;
+                prod_more = next_chunk(prod, ph, st, g);
+                if (!prod_more) break;
+                const SiteS &S = ws.site[g];
+                const int cnt = ph == 0 ? S.nf : S.ns;
+                const int n = min(32, cnt - st * 32);
+                const int4 *src = (ph == 0 ? p.frags + 2 * (S.foff + (long long)st * 32)
+                                           : p.splits + 2 * (S.soff + (long long)st * 32));
+                const int sl = q_issue % RS;
+                if (lane == 0) {
+                    mbar_expect_tx(&ws.bar[sl], (unsigned)n * 32u);
+                    bulk_g2s(&ws.slot[sl][0], src, (unsigned)n * 32u, &ws.bar[sl]);
+                }
+                ++q_issue;
+            }
+        };
+        produce();
+
+        double sum_frag = 0.0, sum_split = 0.0;
+        double acc = 0.0, pend = 0.0;
+        unsigned carryA = 0u, carryB = 0u;
+        int my_pslot = -1, my_pcnt = 0;                 /* lane g: slot / rows / NEW mask of site g's pending chunk */
+        unsigned my_pnew = 0u;
+        int pending = 0;
+        bool all_new = true;
+
+        int c_phase = 0, c_step = 0, c_g = 0;
+        bool have = next_chunk(cons, c_phase, c_step, c_g);
+        while (have) {
+            int n_phase = 0, n_step = 0, n_g = 0;
+            const bool have_next = next_chunk(cons, n_phase, n_step, n_g);
+            const int sl = q_cons % RS;
+            const SiteS &S = ws.site[c_g];
+            const int n = min(32, (c_phase == 0 ? S.nf : S.ns) - c_step * 32);
+            mbar_wait(&ws.bar[sl], (q_cons / RS) & 1u);
+            ++q_cons;
+            int4 *rowp = reinterpret_cast<int4 *>(&ws.slot[sl][0]) + 2 * lane;
+            const bool rv = lane < n;
+            int4 lo = make_int4(0, 0, 0, 0), hi = lo;
+            if (rv) { lo = rowp[0]; hi = rowp[1]; }
+            unsigned nm;
+            if (c_phase == 0) {
+                /* ---------------- phase A, fragment rows ---------------- */
+                const FragOut fo = score_frag_chunk(p, t, S, &ws.win[c_g][0], s_pm, s_lib, hist, lane, n, c_g, m, lo, hi,
+                                                    carryA, carryB, all_new, err);
+                nm = fo.nm;
+                if (rv) {
+                    double2 *dst = reinterpret_cast<double2 *>(rowp);
+                    /* {a + b, LUT indices of a and b (for the CONT / classic replay), p_ref, p_alt} */
+                    dst[0] = make_double2(__dadd_rn(fo.va, fo.vb), __hiloint2double(fo.ib, fo.ia));
+                    dst[1] = make_double2(fo.p_ref, fo.p_alt);
+                }
+            } else {
+                /* ---------------- phase A, split rows (parsers.py:1122-1215) ---------------- */
+                const int4 q0 = lo, q1 = hi;
+                const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
+                const bool swap = (S.tA != S.tB) || (S.posA > S.posB);
+                const int tL = swap ? S.tB : S.tA, tR = swap ? S.tA : S.tB;
+                const int pL = swap ? S.posB : S.posA, pR = swap ? S.posA : S.posB;
+                const int rL = swap ? o2 : o1, rR = swap ? o1 : o2;
+                const int sfl = (q1.z >> 16) & 0xFFFF;
+                const bool soft = sfl & S_SOFT_CLIP;
+                const int cl = rL ? q0.y : q0.z, cr = rR ? q0.y : q0.z;
+                const int dl = rL ? q1.x : q1.y, dr = rR ? q1.x : q1.y;
+                const bool lL = (q0.x == tL) & ((unsigned)(cl - (pL - slop)) <= (unsigned)(2 * slop));
+                const bool lR = (q0.x == tR) & ((unsigned)(cr - (pR - slop)) <= (unsigned)(2 * slop));
+                const bool rLs = (q0.w == tL) & ((unsigned)(dl - (pL - slop)) <= (unsigned)(2 * slop));
+                const bool rRs = (q0.w == tR) & ((unsigned)(dr - (pR - slop)) <= (unsigned)(2 * slop));
+                const bool plain = !soft | (svtype == SV_DEL);
+                const bool dup = soft & (svtype == SV_DUP), inv = soft & (svtype == SV_INV);
+                const bool Ls = (plain & lL) | (dup & lR) | (inv & (lL | lR));
+                const bool Rs = (plain & rRs) | (dup & rLs) | (inv & (rLs | rRs));
+                const double x = s_pm[Ls ? (q1.z & 0xFF) : 0];
+                const double y = s_pm[Rs ? ((q1.z >> 8) & 0xFF) : 0];
+                const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);
+                nm = __ballot_sync(full, rv && (sfl & S_FIRST));
+                const unsigned vm2 = n >= 32 ? full : ((1u << n) - 1u);
+                all_new = all_new && (nm == vm2);
+                if (rv) *reinterpret_cast<double2 *>(rowp) = make_double2(soft ? 0.0 : p_alt, soft ? p_alt : 0.0);
+            }
+            if (lane == c_g) { my_pslot = sl; my_pcnt = n; my_pnew = nm; }
+            ++pending;
+
+            /* ---------------- phase B: close the group ---------------- */
+            const bool phase_ends = !have_next || n_phase != c_phase;
+            if (pending == kGroup || phase_ends || n_step != c_step) {
+                __syncwarp();
+                const int sl_b = __shfl_sync(full, my_pslot, gb);
+                const int cnt_b = __shfl_sync(full, my_pcnt, gb);
+                const unsigned new_b = __shfl_sync(full, my_pnew, gb);
+                if (sl_b >= 0 && c < (c_phase == 0 ? 3 : 2)) {
+                    const unsigned char *base = &ws.slot[sl_b][0];
+                    if (c_phase == 0) {
+                        const double *px = reinterpret_cast<const double *>(base) + (c == 0 ? 0 : c + 1);
+                        if (ASSOC == SVGT_ASSOC_SSO && all_new) {
+#pragma unroll 4
+                            for (int j = 0; j < cnt_b; ++j) {
+                                acc = __dadd_rn(acc, pend);
+                                pend = px[j * 4];
+                            }
+                        } else if (c != 0) {
+                            replay_chain<ASSOC>(px, ws.zero, 0, cnt_b, new_b, false, acc, pend);
+                        } else {
+                            /* ref_seq chain with CONT rows (or classic order): a and b separately */
+                            const int2 *pi = reinterpret_cast<const int2 *>(base + 8);
+                            for (int j = 0; j < cnt_b; ++j) {
+                                const int2 ix = pi[j * 4];                  /* .x = ia (low word), .y = ib */
+                                const double va = s_pm[ix.x], vb = s_pm[ix.y];
+                                if (ASSOC == SVGT_ASSOC_CLASSIC) {
+                                    acc = __dadd_rn(__dadd_rn(acc, va), vb);
+                                } else {
+                                    const bool nw = (new_b >> j) & 1u;
+                                    const double u = nw ? pend : 0.0;
+                                    const double t0 = nw ? 0.0 : pend;
+                                    acc = __dadd_rn(acc, u);
+                                    pend = __dadd_rn(__dadd_rn(t0, va), vb);
+                                }
+                            }
+                        }
+                    } else {
+                        const double *px = reinterpret_cast<const double *>(base) + c;
+                        replay_chain<ASSOC>(px, ws.zero, 0, cnt_b, new_b, all_new, acc, pend);
+                    }
+                }
+                __syncwarp();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* slots go back to the async proxy */
+                q_done += (unsigned)pending;
+                pending = 0;
+                my_pslot = -1;
+                all_new = true;
+                if (phase_ends) {
+                    if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+                    if (c_phase == 0) sum_frag = acc; else sum_split = acc;
+                    acc = 0.0; pend = 0.0;
+                }
+                produce();
+            }
+            c_phase = n_phase; c_step = n_step; c_g = n_g;
+            have = have_next;
+        }
+
+        /* ---- park the five sums in the site's output row (lane 4g+c holds chain c of site g) ---- */
+        if (gb < RG && c < 3) {
+            const long long idx = unit * RG + gb;
+            if (idx < p.n_sites && (ws.site[gb].nf | ws.site[gb].ns)) {
+                const long long site = p.order ? (long long)p.order[idx] : idx;
+                double *row = reinterpret_cast<double *>(p.out + site);
+                if (c == 0) { row[0] = sum_frag; row[1] = sum_split; }
+                else if (c == 1) { row[3] = sum_frag; row[2] = sum_split; }
+                else row[4] = sum_frag;
+            }
+        }
+        __syncwarp();
+    }
+    if (err) {
+        atomicCAS(p.status, 0, err);
+        atomicAdd(p.status + 2, 1);
+    }
+}
+
+size_t ring_smem_bytes(const SvgtParams &p)
+{
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
+    off = (off + 127) & ~(size_t)127;
+    off += sizeof(RingSmem) * kCoopWarps;
+    if (p.hist_in_smem) off += (size_t)p.n_hist * sizeof(unsigned);
+    return off;
+}
+
+}  // namespace
+
+int svgt_launch_ring(const SvgtParams &p, cudaStream_t stream)
+{
+    auto kern = (p.assoc_mode == SVGT_ASSOC_CLASSIC) ? svgt_ring_kernel<SVGT_ASSOC_CLASSIC>
+                                                     : svgt_ring_kernel<SVGT_ASSOC_SSO>;
+    const size_t smem = ring_smem_bytes(p);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SVGT_COOP_THREADS, smem)) != cudaSuccess)
+        return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const long long units = (p.n_sites + RG - 1) / RG;
+    const long long want = (units + kCoopWarps - 1) / kCoopWarps;
+    const long long cap = (long long)sms * per_sm;      /* persistent: one resident wave */
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, SVGT_COOP_THREADS, smem, stream>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    return svgt_launch_call(p, stream);
+}
