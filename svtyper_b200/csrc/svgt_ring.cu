@@ -22,15 +22,24 @@
 namespace {
 
 constexpr int RG = 8;               /* sites per work unit                                        */
-constexpr int RS = 8;               /* ring slots per warp                                         */
-constexpr int kGroup = 4;           /* chunks per phase-B group (RS - kGroup chunks stay in flight) */
-constexpr int kRingSlotBytes = 33 * 32; /* 32 rows + 32 B pad: chain lanes of different sites hit distinct banks */
+constexpr int RS = 4;               /* raw ring slots per warp = chunks in flight                  */
+constexpr int kGroup = 4;           /* chunks per phase-B group = parked slots                     */
+constexpr int kParkBytes = 33 * 32; /* 32 rows + 32 B pad: chain lanes of different sites hit distinct banks */
+constexpr int kFifo = 8;            /* chunk descriptors handed from the issue side to the scoring side */
+
+/* issue side -> scoring side, one per chunk in flight (warp-uniform) */
+struct ChunkDesc { int n, g, tag, pad; };   /* rows, site, phase << 24 | step (tag -1 = end of unit) */
+/* scoring side -> chain lanes, one per site (warp-uniform) */
+struct Pending { int slot_cnt; unsigned newmask; };   /* (parked slot + 1) << 8 | rows, 0 = nothing pending */
 
 struct alignas(128) RingSmem {
     SiteS site[RG];
     Win win[RG][kWLibs];
-    unsigned char slot[RS][kRingSlotBytes];
+    unsigned char raw[RS][1024];            /* cp.async.bulk targets                    */
+    unsigned char park[kGroup][kParkBytes]; /* phase A -> phase B                        */
     unsigned long long bar[RS];
+    ChunkDesc desc[kFifo];
+    Pending pend[RG];
     double zero[2];
 };
 
@@ -108,7 +117,9 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
 
     const int gb = lane >> 2, c = lane & 3;                /* phase-B role: chain c of site gb */
     const long long n_units = (p.n_sites + RG - 1) / RG;
-    unsigned q_issue = 0, q_cons = 0, q_done = 0;           /* running chunk counters of this warp */
+    /* running counters of this warp: FIFO entries (chunks + one end-of-unit sentinel per unit) and
+     * chunks proper (ring slot and mbarrier phase follow the latter) */
+    unsigned f_issue = 0, f_cons = 0, q_issue = 0, q_cons = 0;
 
     for (;;) {
         long long unit = 0;
@@ -156,79 +167,77 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
             __syncwarp();
         }
 
-        /* ---- the unit's chunk stream: two cursors over the same sequence ---- */
-        auto next_chunk = [&](Cursor &cu, int &phase, int &step, int &g) -> bool {
-            for (;;) {
-                if (cu.mask) {
-                    g = __ffs(cu.mask) - 1;
-                    cu.mask &= cu.mask - 1u;
-                    phase = cu.phase; step = cu.step;
-                    return true;
-                }
-                ++cu.step;
-                const unsigned mk = __ballot_sync(full, (cu.phase == 0 ? my_nf : my_ns) > cu.step * 32);
-                if (mk) { cu.mask = mk; continue; }
-                if (cu.phase == 0) { cu.phase = 1; cu.step = -1; continue; }
-                return false;
-            }
-        };
-        Cursor prod = {0, -1, 0u}, cons = {0, -1, 0u};
+        /* ---- issue side: a cursor over the unit's chunk stream (fragment chunks step-major, then
+         *      split chunks), one cp.async.bulk per chunk, descriptor into the FIFO ---- */
+        Cursor prod = {0, -1, 0u};
         bool prod_more = true;
-        auto produce = [&]() {
-            /* issue bulk copies while a slot is free (chunks q_done .. q_issue-1 occupy slots) */
-            while (prod_more && (q_issue - q_done) < (unsigned)RS) {
-                int ph, st, g;
-                prod_more = next_chunk(prod, ph, st, g);
-                if (!prod_more) break;
+        auto issue_one = [&]() {
+            if (!prod_more) return;
+            int ph = 0, st = 0, g = 0;
+            for (;;) {
+                if (prod.mask) {
+                    g = __ffs(prod.mask) - 1;
+                    prod.mask &= prod.mask - 1u;
+                    ph = prod.phase; st = prod.step;
+                    break;
+                }
+                ++prod.step;
+                const unsigned mk = __ballot_sync(full, (prod.phase == 0 ? my_nf : my_ns) > prod.step * 32);
+                if (mk) { prod.mask = mk; continue; }
+                if (prod.phase == 0) { prod.phase = 1; prod.step = -1; continue; }
+                prod_more = false;
+                break;
+            }
+            ChunkDesc d;
+            if (prod_more) {
                 const SiteS &S = ws.site[g];
                 const int cnt = ph == 0 ? S.nf : S.ns;
-                const int n = min(32, cnt - st * 32);
+                d.n = min(32, cnt - st * 32); d.g = g; d.tag = (ph << 24) | st; d.pad = 0;
                 const int4 *src = (ph == 0 ? p.frags + 2 * (S.foff + (long long)st * 32)
                                            : p.splits + 2 * (S.soff + (long long)st * 32));
                 const int sl = q_issue % RS;
                 if (lane == 0) {
-                    mbar_expect_tx(&ws.bar[sl], (unsigned)n * 32u);
-                    bulk_g2s(&ws.slot[sl][0], src, (unsigned)n * 32u, &ws.bar[sl]);
+                    mbar_expect_tx(&ws.bar[sl], (unsigned)d.n * 32u);
+                    bulk_g2s(&ws.raw[sl][0], src, (unsigned)d.n * 32u, &ws.bar[sl]);
                 }
-                ++q_issue;
+            } else {
+                d.n = 0; d.g = 0; d.tag = -1; d.pad = 0;
             }
+            if (lane == 0) *reinterpret_cast<int4 *>(&ws.desc[f_issue % kFifo]) = make_int4(d.n, d.g, d.tag, 0);
+            ++f_issue;
+            if (prod_more) ++q_issue;
         };
-        produce();
+        for (int i = 0; i < RS; ++i) issue_one();
+        __syncwarp();
 
         double sum_frag = 0.0, sum_split = 0.0;
         double acc = 0.0, pend = 0.0;
         unsigned carryA = 0u, carryB = 0u;
-        int my_pslot = -1, my_pcnt = 0;                 /* lane g: slot / rows / NEW mask of site g's pending chunk */
-        unsigned my_pnew = 0u;
         int pending = 0;
         bool all_new = true;
 
-        int c_phase = 0, c_step = 0, c_g = 0;
-        bool have = next_chunk(cons, c_phase, c_step, c_g);
-        while (have) {
-            int n_phase = 0, n_step = 0, n_g = 0;
-            const bool have_next = next_chunk(cons, n_phase, n_step, n_g);
+        for (;;) {
+            const int4 dq = *reinterpret_cast<const int4 *>(&ws.desc[f_cons % kFifo]);     /* n g tag */
+            if (dq.z < 0) { ++f_cons; break; }                                             /* end of unit */
+            const int n = dq.x, c_g = dq.y, c_phase = dq.z >> 24;
             const int sl = q_cons % RS;
-            const SiteS &S = ws.site[c_g];
-            const int n = min(32, (c_phase == 0 ? S.nf : S.ns) - c_step * 32);
             mbar_wait(&ws.bar[sl], (q_cons / RS) & 1u);
-            ++q_cons;
-            int4 *rowp = reinterpret_cast<int4 *>(&ws.slot[sl][0]) + 2 * lane;
+            const int4 *rowp = reinterpret_cast<const int4 *>(&ws.raw[sl][0]) + 2 * lane;
             const bool rv = lane < n;
             int4 lo = make_int4(0, 0, 0, 0), hi = lo;
             if (rv) { lo = rowp[0]; hi = rowp[1]; }
+            const SiteS &S = ws.site[c_g];
+            unsigned char *parkp = &ws.park[pending][0] + 32 * lane;
             unsigned nm;
             if (c_phase == 0) {
                 /* ---------------- phase A, fragment rows ---------------- */
                 const FragOut fo = score_frag_chunk(p, t, S, &ws.win[c_g][0], s_pm, s_lib, hist, lane, n, c_g, m, lo, hi,
                                                     carryA, carryB, all_new, err);
                 nm = fo.nm;
-                if (rv) {
-                    double2 *dst = reinterpret_cast<double2 *>(rowp);
-                    /* {a + b, LUT indices of a and b (for the CONT / classic replay), p_ref, p_alt} */
-                    dst[0] = make_double2(__dadd_rn(fo.va, fo.vb), __hiloint2double(fo.ib, fo.ia));
-                    dst[1] = make_double2(fo.p_ref, fo.p_alt);
-                }
+                /* {a + b, LUT indices of a and b (for the CONT / classic replay), p_ref, p_alt} */
+                double2 *dst = reinterpret_cast<double2 *>(parkp);
+                dst[0] = make_double2(__dadd_rn(fo.va, fo.vb), __hiloint2double(fo.ib, fo.ia));
+                dst[1] = make_double2(fo.p_ref, fo.p_alt);
             } else {
                 /* ---------------- phase A, split rows (parsers.py:1122-1215) ---------------- */
                 const int4 q0 = lo, q1 = hi;
@@ -247,28 +256,38 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
                 const bool rRs = (q0.w == tR) & ((unsigned)(dr - (pR - slop)) <= (unsigned)(2 * slop));
                 const bool plain = !soft | (svtype == SV_DEL);
                 const bool dup = soft & (svtype == SV_DUP), inv = soft & (svtype == SV_INV);
-                const bool Ls = (plain & lL) | (dup & lR) | (inv & (lL | lR));
-                const bool Rs = (plain & rRs) | (dup & rLs) | (inv & (rLs | rRs));
+                const bool Ls = rv & ((plain & lL) | (dup & lR) | (inv & (lL | lR)));
+                const bool Rs = rv & ((plain & rRs) | (dup & rLs) | (inv & (rLs | rRs)));
                 const double x = s_pm[Ls ? (q1.z & 0xFF) : 0];
                 const double y = s_pm[Rs ? ((q1.z >> 8) & 0xFF) : 0];
                 const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);
                 nm = __ballot_sync(full, rv && (sfl & S_FIRST));
                 const unsigned vm2 = n >= 32 ? full : ((1u << n) - 1u);
                 all_new = all_new && (nm == vm2);
-                if (rv) *reinterpret_cast<double2 *>(rowp) = make_double2(soft ? 0.0 : p_alt, soft ? p_alt : 0.0);
+                *reinterpret_cast<double2 *>(parkp) = make_double2(soft ? 0.0 : p_alt, soft ? p_alt : 0.0);
             }
-            if (lane == c_g) { my_pslot = sl; my_pcnt = n; my_pnew = nm; }
+            if (lane == 0) {
+                Pending pd;
+                pd.slot_cnt = ((pending + 1) << 8) | n;
+                pd.newmask = nm;
+                *reinterpret_cast<int2 *>(&ws.pend[c_g]) = make_int2(pd.slot_cnt, (int)pd.newmask);
+            }
             ++pending;
+            ++q_cons;
+            ++f_cons;
+            /* the rows of this chunk are in registers (their values have been used above): refill its slot */
+            issue_one();
+            __syncwarp();
 
             /* ---------------- phase B: close the group ---------------- */
-            const bool phase_ends = !have_next || n_phase != c_phase;
-            if (pending == kGroup || phase_ends || n_step != c_step) {
-                __syncwarp();
-                const int sl_b = __shfl_sync(full, my_pslot, gb);
-                const int cnt_b = __shfl_sync(full, my_pcnt, gb);
-                const unsigned new_b = __shfl_sync(full, my_pnew, gb);
+            const int n_tag = ws.desc[f_cons % kFifo].tag;          /* the chunk after this one, or -1 */
+            const bool phase_ends = n_tag < 0 || (n_tag >> 24) != c_phase;
+            if (pending == kGroup || n_tag != dq.z) {
+                const int2 pd = *reinterpret_cast<const int2 *>(&ws.pend[gb]);
+                const int sl_b = (pd.x >> 8) - 1, cnt_b = pd.x & 0xFF;
+                const unsigned new_b = (unsigned)pd.y;
                 if (sl_b >= 0 && c < (c_phase == 0 ? 3 : 2)) {
-                    const unsigned char *base = &ws.slot[sl_b][0];
+                    const unsigned char *base = &ws.park[sl_b][0];
                     if (c_phase == 0) {
                         const double *px = reinterpret_cast<const double *>(base) + (c == 0 ? 0 : c + 1);
                         if (ASSOC == SVGT_ASSOC_SSO && all_new) {
@@ -302,20 +321,16 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
                     }
                 }
                 __syncwarp();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* slots go back to the async proxy */
-                q_done += (unsigned)pending;
+                if (lane < RG) ws.pend[lane].slot_cnt = 0;
                 pending = 0;
-                my_pslot = -1;
                 all_new = true;
                 if (phase_ends) {
                     if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
                     if (c_phase == 0) sum_frag = acc; else sum_split = acc;
                     acc = 0.0; pend = 0.0;
                 }
-                produce();
+                __syncwarp();
             }
-            c_phase = n_phase; c_step = n_step; c_g = n_g;
-            have = have_next;
         }
 
         /* ---- park the five sums in the site's output row (lane 4g+c holds chain c of site g) ---- */
