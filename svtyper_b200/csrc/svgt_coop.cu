@@ -142,7 +142,6 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
         {
             double acc = 0.0, pend = 0.0;
             unsigned carryA = 0u, carryB = 0u;      /* EXTRA-run hits carried into the next step, bit g */
-            bool all_new = true;
             const int my_nf = lane < G ? ws.site[lane].nf : 0;
 
             /* chunk iterator (warp-uniform): step-major over the sites that still have rows */
@@ -178,13 +177,10 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 asm volatile("membar.cta;" ::: "memory");
 #endif
                 const int n = ws.site[g].nf - step * 32;
-                const FragOut fo = score_frag_chunk(p, t, ws.site[g], &ws.win[g][0], s_pm, s_lib, hist, lane, n, g, m, lo, hi,
-                                                    carryA, carryB, all_new, err);
-                const double va = fo.va, vb = fo.vb, p_ref = fo.p_ref, p_alt = fo.p_alt;
-                const unsigned nm = fo.nm;
-                double4 *dst = reinterpret_cast<double4 *>(&ws.contrib[g][lane][0]);
-                *dst = make_double4(va, vb, p_ref, p_alt);
-                if (lane == 0) ws.newmask[g] = nm;
+                const FragOut fo = score_frag_chunk<ASSOC>(p, t, ws.site[g], &ws.win[g][0], s_pm, s_lib, hist, lane, n, g, m,
+                                                           lo, hi, carryA, carryB, err);
+                park_frag(&ws.contrib[g][lane][0], fo);
+                if (lane == 0) ws.newmask[g] = (unsigned)fo.lead;
 #ifdef SVGT_MARK
                 asm volatile("membar.cta;" ::: "memory");
 #endif
@@ -195,17 +191,13 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     if (gb < G && c < 3) {
                         int cnt = ws.site[gb].nf - step * 32;
                         cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
-                        const double *row0 = &ws.contrib[gb][0][0];
-                        const double *px = row0 + (c == 0 ? 0 : c + 1);
-                        const double *py = (c == 0) ? row0 + 1 : ws.zero;
 #if !(SVGT_DIAG & 2)
-                        replay_chain<ASSOC>(px, py, c == 0 ? 4 : 0, cnt, ws.newmask[gb], all_new, acc, pend);
+                        replay_frag<ASSOC>(&ws.contrib[gb][0][0], c, cnt, (int)ws.newmask[gb], s_pm, acc, pend);
 #else
-                        acc += px[0] + py[0] + cnt;
+                        acc += ws.contrib[gb][0][c] + cnt;
 #endif
                     }
                     __syncwarp();
-                    all_new = true;
                 }
             };
 #if SVGT_ROWBUFS == 3
@@ -270,7 +262,6 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     q0 = ldg4(rp); q1 = ldg4(rp + 1);
                 }
             };
-            bool all_new = true;
             int ss0 = 0, sg0 = 0, ss1 = 0, sg1 = 0, ss2 = 0, sg2 = 0;
             int4 a0, b0, a1, b1, a2, b2;
             bool e0 = advance_split(ss0, sg0);
@@ -285,46 +276,18 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     const int4 q0 = a0, q1 = b0;
                     const SiteS &S = ws.site[g];
                     const int n = min(32, S.ns - step * 32);
-                    const bool rv = lane < n;
-                    /* arrange breakends left to right, parsers.py:1143-1161 */
-                    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
-                    const bool swap = (S.tA != S.tB) || (S.posA > S.posB);
-                    const int tL = swap ? S.tB : S.tA, tR = swap ? S.tA : S.tB;
-                    const int pL = swap ? S.posB : S.posA, pR = swap ? S.posA : S.posB;
-                    const int rL = swap ? o2 : o1, rR = swap ? o1 : o2;
-                    const int sfl = (q1.z >> 16) & 0xFFFF;
-                    const bool soft = sfl & S_SOFT_CLIP;
-                    const int cl = rL ? q0.y : q0.z, cr = rR ? q0.y : q0.z;       /* left piece vs L / R side */
-                    const int dl = rL ? q1.x : q1.y, dr = rR ? q1.x : q1.y;       /* right piece vs L / R side */
-                    const bool lL = (q0.x == tL) & ((unsigned)(cl - (pL - slop)) <= (unsigned)(2 * slop));
-                    const bool lR = (q0.x == tR) & ((unsigned)(cr - (pR - slop)) <= (unsigned)(2 * slop));
-                    const bool rLs = (q0.w == tL) & ((unsigned)(dl - (pL - slop)) <= (unsigned)(2 * slop));
-                    const bool rRs = (q0.w == tR) & ((unsigned)(dr - (pR - slop)) <= (unsigned)(2 * slop));
-                    const bool plain = !soft | (svtype == SV_DEL);
-                    const bool dup = soft & (svtype == SV_DUP), inv = soft & (svtype == SV_INV);
-                    const bool Ls = (plain & lL) | (dup & lR) | (inv & (lL | lR));
-                    const bool Rs = (plain & rRs) | (dup & rLs) | (inv & (rLs | rRs));
-                    const double x = Ls ? s_pm[q1.z & 0xFF] : 0.0;
-                    const double y = Rs ? s_pm[(q1.z >> 8) & 0xFF] : 0.0;
-                    double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);
-                    if (!rv) p_alt = 0.0;
-                    const unsigned nm = __ballot_sync(full, rv && (sfl & S_FIRST));
-                    const unsigned vm2 = n == 32 ? full : ((1u << n) - 1u);
-                    all_new = all_new && (nm == vm2);
-                    double2 *dst = reinterpret_cast<double2 *>(&ws.contrib[g][lane][0]);
-                    *dst = make_double2(soft ? 0.0 : p_alt, soft ? p_alt : 0.0);
-                    if (lane == 0) ws.newmask[g] = nm;
+                    const SplitOut so = score_split_chunk<ASSOC>(S, s_pm, lane, n, slop, q0, q1);
+                    *reinterpret_cast<double2 *>(&ws.contrib[g][lane][0]) = make_double2(so.vseq, so.vclip);
+                    if (lane == 0) ws.newmask[g] = (unsigned)so.lead;
                 }
                 if (!e1 || ss1 != ss0) {                        /* last chunk of its super-step: phase B */
                     __syncwarp();
                     if (gb < G && c < 2) {
                         int cnt = ws.site[gb].ns - ss0 * 32;
                         cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
-                        const double *px = &ws.contrib[gb][0][0] + c;
-                        replay_chain<ASSOC>(px, ws.zero, 0, cnt, ws.newmask[gb], all_new, acc, pend);
+                        replay_split<ASSOC>(&ws.contrib[gb][0][0], c, cnt, (int)ws.newmask[gb], acc, pend);
                     }
                     __syncwarp();
-                    all_new = true;
                 }
                 ss0 = ss1; sg0 = sg1; a0 = a1; b0 = b1; e0 = e1;
                 ss1 = ss2; sg1 = sg2; a1 = a2; b1 = b2; e1 = e2;

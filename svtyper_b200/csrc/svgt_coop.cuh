@@ -311,16 +311,27 @@ __device__ __forceinline__ void pe_chain(int a_start, int b_end, int tidA, int t
 
 /* one 32-row fragment chunk of site S scored by the warp (phase A): what every lane parks for its row */
 struct FragOut {
-    double va, vb, p_ref, p_alt;    /* ref_seq addends of read A / read B, ref_span and alt_span addends */
-    int ia, ib;                     /* the prob_mapq LUT indices behind va / vb (0 = none)               */
-    unsigned nm;                    /* warp-uniform: bit j = row j starts a new fragment (not CONT/EXTRA) */
+    double s, p_ref, p_alt;         /* ref_seq / ref_span / alt_span addends this row parks (see below)     */
+    int ia, ib;                     /* prob_mapq LUT indices of the row's own ref_seq addends a, b (0 = none) */
+    int lead;                       /* warp-uniform: leading rows that continue the previous chunk's fragment */
 };
 
+/*
+ * Continuation rows are resolved HERE, lane-parallel, so that phase B is one add per row:
+ * in the sso order (singlesample.py:254-259, :367-378) a fragment's reads are summed into a sub-total
+ * first -- sub = ((0 + a1) + b1) + a2 ... over its rows (CONT rows; EXTRA interval rows add nothing) --
+ * and the sub-total is added to the site sum when the next fragment starts.  Each fragment's FIRST row
+ * gathers the addends of its continuation rows with shuffles, in row order, and parks the finished
+ * sub-total; the absorbed rows park 0.0 (x + 0.0 is exact), so phase B just does acc += pend, pend = s
+ * for every row.  Only continuation rows at the very start of a chunk (their fragment began in the
+ * previous chunk) are left to phase B: `lead` of them update the carried sub-total first.
+ */
+template <int ASSOC>
 __device__ __forceinline__ FragOut score_frag_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const Win *wins,
                                                     const double *s_pm, const LibK *s_lib, const unsigned *hist,
                                                     const int lane, const int n, const int g, const int m,
                                                     const int4 lo, const int4 hi, unsigned &carryA, unsigned &carryB,
-                                                    bool &all_new, int &err)
+                                                    int &err)
 {
     const unsigned full = 0xffffffffu;
         const int4 s0 = *reinterpret_cast<const int4 *>(&S.tA);   /* tA tB wA0 wA1 */
@@ -396,7 +407,6 @@ __device__ __forceinline__ FragOut score_frag_chunk(const SvgtParams &p, const T
             carryA = (carryA & ~(1u << g)) | ((unsigned)nA << g);
             carryB = (carryB & ~(1u << g)) | ((unsigned)nB << g);
             nm = __ballot_sync(full, rv && !(fl & (F_CONT | F_EXTRA)));
-            all_new = all_new && (nm == vm);
             if (isx) { hitA = 0; hitB = 0; }
 #ifdef SVGT_MARK
             asm volatile("membar.cta;" ::: "memory");
@@ -460,39 +470,142 @@ __device__ __forceinline__ FragOut score_frag_chunk(const SvgtParams &p, const T
         const double p_alt = __dmul_rn(s_pm[idx_alt], pmB);
         const double p_ref = __dmul_rn(s_pm[idx_ref], s_pm[idx_refB]);
     FragOut o;
-    o.va = va; o.vb = vb; o.p_ref = p_ref; o.p_alt = p_alt;
+    o.s = __dadd_rn(va, vb); o.p_ref = p_ref; o.p_alt = p_alt;
     o.ia = hitA ? mqA : 0; o.ib = hitB ? mqB : 0;
-    o.nm = nm;
+    o.lead = 0;
+    if (ASSOC == SVGT_ASSOC_SSO && nm != vm) {          /* the chunk has CONT / EXTRA rows (warp-uniform) */
+        const unsigned NN = vm & ~nm;                   /* rows that continue a fragment            */
+        o.lead = nm ? __ffs(nm) - 1 : n;
+        const bool nonnew = (NN >> lane) & 1u;
+        /* a continuation row normally carries no paired-end weight; if one does, gather those too */
+        const bool pe_too = __ballot_sync(full, nonnew && (p_ref != 0.0 || p_alt != 0.0)) != 0u;
+        bool alive = rv && !nonnew;
+        for (int k = 1; k < 32; ++k) {
+            alive = alive && (lane + k < 32) && ((NN >> (lane + k < 32 ? lane + k : 31)) & 1u);
+            if (!__any_sync(full, alive)) break;
+            const double ak = __shfl_down_sync(full, va, k), bk = __shfl_down_sync(full, vb, k);
+            if (alive) o.s = __dadd_rn(__dadd_rn(o.s, ak), bk);
+            if (pe_too) {
+                const double rk = __shfl_down_sync(full, p_ref, k), qk = __shfl_down_sync(full, p_alt, k);
+                if (alive) { o.p_ref = __dadd_rn(o.p_ref, rk); o.p_alt = __dadd_rn(o.p_alt, qk); }
+            }
+        }
+        if (nonnew && lane >= o.lead) { o.s = 0.0; o.p_ref = 0.0; o.p_alt = 0.0; }   /* absorbed by its first row */
+    }
     return o;
 }
 
-/* ordered replay of one chain over `cnt` parked rows (phase B).
- * SSO:     per row   if NEW: acc += pend, pend = 0;   pend = (pend + x) + y
- * CLASSIC: per row   acc = (acc + x) + y
- * NEW rows dominate, so the all-NEW case is a 2-add loop. */
-template <int ASSOC>
-__device__ __forceinline__ void replay_chain(const double *px, const double *py, int ystride, int cnt, unsigned newm,
-                                             bool all_new, double &acc, double &pend)
+/* park a scored fragment row for phase B: {s, LUT indices of a and b, p_ref, p_alt} (32 B) */
+__device__ __forceinline__ void park_frag(void *dst32, const FragOut &o)
 {
+    double2 *d = reinterpret_cast<double2 *>(dst32);
+    d[0] = make_double2(o.s, __hiloint2double(o.ib, o.ia));
+    d[1] = make_double2(o.p_ref, o.p_alt);
+}
+
+/* phase B of one fragment chunk for chain c (0 ref_seq, 1 ref_span, 2 alt_span) of one site */
+template <int ASSOC>
+__device__ __forceinline__ void replay_frag(const void *base, int c, int cnt, int lead, const double *s_pm, double &acc,
+                                            double &pend)
+{
+    const double *px = reinterpret_cast<const double *>(base) + (c == 0 ? 0 : c + 1);
+    const int2 *pi = reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(base) + 8);   /* .x = ia, .y = ib */
+    if (ASSOC == SVGT_ASSOC_CLASSIC) {
+        /* classic.py:306-311,339-408: every read goes straight into the site sum */
+        if (c == 0) {
+            for (int j = 0; j < cnt; ++j) {
+                const int2 ix = pi[j * 4];
+                acc = __dadd_rn(__dadd_rn(acc, s_pm[ix.x]), s_pm[ix.y]);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 4]);
+        }
+        lead = cnt;                                     /* nothing left for the sso loops below */
+    }
+    for (int j = 0; j < (ASSOC == SVGT_ASSOC_CLASSIC ? 0 : lead); ++j) {                    /* rows continuing the previous chunk's last fragment */
+        if (c == 0) {
+            const int2 ix = pi[j * 4];
+            pend = __dadd_rn(__dadd_rn(pend, s_pm[ix.x]), s_pm[ix.y]);
+        } else {
+            pend = __dadd_rn(pend, px[j * 4]);
+        }
+    }
+#pragma unroll 4
+    for (int j = lead; j < cnt; ++j) {
+        acc = __dadd_rn(acc, pend);
+        pend = px[j * 4];
+    }
+}
+
+/* one 32-row split chunk (parsers.py:1122-1215, singlesample.py:262-274): parks {alt_seq, alt_clip}
+ * addends; rows that are not the FIRST split of their fragment are folded into the first one's
+ * sub-totals exactly as above */
+struct SplitOut { double vseq, vclip; int lead; };
+
+template <int ASSOC>
+__device__ __forceinline__ SplitOut score_split_chunk(const SiteS &S, const double *s_pm, const int lane, const int n,
+                                                      const int slop, const int4 q0, const int4 q1)
+{
+    const unsigned full = 0xffffffffu;
+    const bool rv = lane < n;
+    const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
+    /* arrange breakends left to right, parsers.py:1143-1161 */
+    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
+    const bool swap = (S.tA != S.tB) || (S.posA > S.posB);
+    const int tL = swap ? S.tB : S.tA, tR = swap ? S.tA : S.tB;
+    const int pL = swap ? S.posB : S.posA, pR = swap ? S.posA : S.posB;
+    const int rL = swap ? o2 : o1, rR = swap ? o1 : o2;
+    const int sfl = rv ? ((q1.z >> 16) & 0xFFFF) : S_FIRST;
+    const bool soft = sfl & S_SOFT_CLIP;
+    const int cl = rL ? q0.y : q0.z, cr = rR ? q0.y : q0.z;       /* left piece vs L / R side */
+    const int dl = rL ? q1.x : q1.y, dr = rR ? q1.x : q1.y;       /* right piece vs L / R side */
+    const bool lL = (q0.x == tL) & ((unsigned)(cl - (pL - slop)) <= (unsigned)(2 * slop));
+    const bool lR = (q0.x == tR) & ((unsigned)(cr - (pR - slop)) <= (unsigned)(2 * slop));
+    const bool rLs = (q0.w == tL) & ((unsigned)(dl - (pL - slop)) <= (unsigned)(2 * slop));
+    const bool rRs = (q0.w == tR) & ((unsigned)(dr - (pR - slop)) <= (unsigned)(2 * slop));
+    const bool plain = !soft | (svtype == SV_DEL);
+    const bool dup = soft & (svtype == SV_DUP), inv = soft & (svtype == SV_INV);
+    const bool Ls = rv & ((plain & lL) | (dup & lR) | (inv & (lL | lR)));
+    const bool Rs = rv & ((plain & rRs) | (dup & rLs) | (inv & (rLs | rRs)));
+    const double x = s_pm[Ls ? (q1.z & 0xFF) : 0];
+    const double y = s_pm[Rs ? ((q1.z >> 8) & 0xFF) : 0];
+    const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);       /* (.. + ..) / 2.0, exact either way */
+    SplitOut o;
+    o.vseq = soft ? 0.0 : p_alt; o.vclip = soft ? p_alt : 0.0; o.lead = 0;
+    const unsigned nm = __ballot_sync(full, rv && (sfl & S_FIRST));
+    if (ASSOC == SVGT_ASSOC_SSO && nm != vm) {
+        const unsigned NN = vm & ~nm;
+        o.lead = nm ? __ffs(nm) - 1 : n;
+        const bool nonnew = (NN >> lane) & 1u;
+        const double vs0 = o.vseq, vc0 = o.vclip;
+        bool alive = rv && !nonnew;
+        for (int k = 1; k < 32; ++k) {
+            alive = alive && (lane + k < 32) && ((NN >> (lane + k < 32 ? lane + k : 31)) & 1u);
+            if (!__any_sync(full, alive)) break;
+            const double sk = __shfl_down_sync(full, vs0, k), ck = __shfl_down_sync(full, vc0, k);
+            if (alive) { o.vseq = __dadd_rn(o.vseq, sk); o.vclip = __dadd_rn(o.vclip, ck); }
+        }
+        if (nonnew && lane >= o.lead) { o.vseq = 0.0; o.vclip = 0.0; }
+    }
+    return o;
+}
+
+/* phase B of one split chunk for chain c (0 alt_seq, 1 alt_clip) */
+template <int ASSOC>
+__device__ __forceinline__ void replay_split(const void *base, int c, int cnt, int lead, double &acc, double &pend)
+{
+    const double *px = reinterpret_cast<const double *>(base) + c;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
 #pragma unroll 4
-        for (int j = 0; j < cnt; ++j)
-            acc = __dadd_rn(__dadd_rn(acc, px[j * 4]), py[j * ystride]);
-    } else if (all_new) {
+        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 4]);
+        lead = cnt;
+    }
+    for (int j = 0; j < (ASSOC == SVGT_ASSOC_CLASSIC ? 0 : lead); ++j) pend = __dadd_rn(pend, px[j * 4]);
 #pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            const double tsum = __dadd_rn(px[j * 4], py[j * ystride]);
-            acc = __dadd_rn(acc, pend);
-            pend = tsum;
-        }
-    } else {
-        for (int j = 0; j < cnt; ++j) {
-            const bool nw = (newm >> j) & 1u;
-            const double u = nw ? pend : 0.0;
-            const double t0 = nw ? 0.0 : pend;
-            acc = __dadd_rn(acc, u);
-            pend = __dadd_rn(__dadd_rn(t0, px[j * 4]), py[j * ystride]);
-        }
+    for (int j = lead; j < cnt; ++j) {
+        acc = __dadd_rn(acc, pend);
+        pend = px[j * 4];
     }
 }
 

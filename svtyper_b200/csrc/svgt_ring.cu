@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
     RingSmem &ws = s_warp[warp];
     if (lane < 2) ws.zero[lane] = 0.0;
     if (lane < RS) mbar_init(&ws.bar[lane], 1);
+    if (lane < RG) { ws.pend[lane].slot_cnt = 0; ws.pend[lane].newmask = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const bool small_counts = __syncthreads_or(big) == 0;
 
@@ -214,7 +215,6 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
         double acc = 0.0, pend = 0.0;
         unsigned carryA = 0u, carryB = 0u;
         int pending = 0;
-        bool all_new = true;
 
         for (;;) {
             const int4 dq = *reinterpret_cast<const int4 *>(&ws.desc[f_cons % kFifo]);     /* n g tag */
@@ -228,48 +228,23 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
             if (rv) { lo = rowp[0]; hi = rowp[1]; }
             const SiteS &S = ws.site[c_g];
             unsigned char *parkp = &ws.park[pending][0] + 32 * lane;
-            unsigned nm;
+            int lead;
             if (c_phase == 0) {
                 /* ---------------- phase A, fragment rows ---------------- */
-                const FragOut fo = score_frag_chunk(p, t, S, &ws.win[c_g][0], s_pm, s_lib, hist, lane, n, c_g, m, lo, hi,
-                                                    carryA, carryB, all_new, err);
-                nm = fo.nm;
-                /* {a + b, LUT indices of a and b (for the CONT / classic replay), p_ref, p_alt} */
-                double2 *dst = reinterpret_cast<double2 *>(parkp);
-                dst[0] = make_double2(__dadd_rn(fo.va, fo.vb), __hiloint2double(fo.ib, fo.ia));
-                dst[1] = make_double2(fo.p_ref, fo.p_alt);
+                const FragOut fo = score_frag_chunk<ASSOC>(p, t, S, &ws.win[c_g][0], s_pm, s_lib, hist, lane, n, c_g, m, lo, hi,
+                                                           carryA, carryB, err);
+                park_frag(parkp, fo);
+                lead = fo.lead;
             } else {
-                /* ---------------- phase A, split rows (parsers.py:1122-1215) ---------------- */
-                const int4 q0 = lo, q1 = hi;
-                const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
-                const bool swap = (S.tA != S.tB) || (S.posA > S.posB);
-                const int tL = swap ? S.tB : S.tA, tR = swap ? S.tA : S.tB;
-                const int pL = swap ? S.posB : S.posA, pR = swap ? S.posA : S.posB;
-                const int rL = swap ? o2 : o1, rR = swap ? o1 : o2;
-                const int sfl = (q1.z >> 16) & 0xFFFF;
-                const bool soft = sfl & S_SOFT_CLIP;
-                const int cl = rL ? q0.y : q0.z, cr = rR ? q0.y : q0.z;
-                const int dl = rL ? q1.x : q1.y, dr = rR ? q1.x : q1.y;
-                const bool lL = (q0.x == tL) & ((unsigned)(cl - (pL - slop)) <= (unsigned)(2 * slop));
-                const bool lR = (q0.x == tR) & ((unsigned)(cr - (pR - slop)) <= (unsigned)(2 * slop));
-                const bool rLs = (q0.w == tL) & ((unsigned)(dl - (pL - slop)) <= (unsigned)(2 * slop));
-                const bool rRs = (q0.w == tR) & ((unsigned)(dr - (pR - slop)) <= (unsigned)(2 * slop));
-                const bool plain = !soft | (svtype == SV_DEL);
-                const bool dup = soft & (svtype == SV_DUP), inv = soft & (svtype == SV_INV);
-                const bool Ls = rv & ((plain & lL) | (dup & lR) | (inv & (lL | lR)));
-                const bool Rs = rv & ((plain & rRs) | (dup & rLs) | (inv & (rLs | rRs)));
-                const double x = s_pm[Ls ? (q1.z & 0xFF) : 0];
-                const double y = s_pm[Rs ? ((q1.z >> 8) & 0xFF) : 0];
-                const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);
-                nm = __ballot_sync(full, rv && (sfl & S_FIRST));
-                const unsigned vm2 = n >= 32 ? full : ((1u << n) - 1u);
-                all_new = all_new && (nm == vm2);
-                *reinterpret_cast<double2 *>(parkp) = make_double2(soft ? 0.0 : p_alt, soft ? p_alt : 0.0);
+                /* ---------------- phase A, split rows ---------------- */
+                const SplitOut so = score_split_chunk<ASSOC>(S, s_pm, lane, n, slop, lo, hi);
+                *reinterpret_cast<double2 *>(parkp) = make_double2(so.vseq, so.vclip);
+                lead = so.lead;
             }
             if (lane == 0) {
                 Pending pd;
                 pd.slot_cnt = ((pending + 1) << 8) | n;
-                pd.newmask = nm;
+                pd.newmask = (unsigned)lead;
                 *reinterpret_cast<int2 *>(&ws.pend[c_g]) = make_int2(pd.slot_cnt, (int)pd.newmask);
             }
             ++pending;
@@ -285,45 +260,14 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, 2) svgt_ring_kernel(const S
             if (pending == kGroup || n_tag != dq.z) {
                 const int2 pd = *reinterpret_cast<const int2 *>(&ws.pend[gb]);
                 const int sl_b = (pd.x >> 8) - 1, cnt_b = pd.x & 0xFF;
-                const unsigned new_b = (unsigned)pd.y;
+                const int lead_b = pd.y;
                 if (sl_b >= 0 && c < (c_phase == 0 ? 3 : 2)) {
-                    const unsigned char *base = &ws.park[sl_b][0];
-                    if (c_phase == 0) {
-                        const double *px = reinterpret_cast<const double *>(base) + (c == 0 ? 0 : c + 1);
-                        if (ASSOC == SVGT_ASSOC_SSO && all_new) {
-#pragma unroll 4
-                            for (int j = 0; j < cnt_b; ++j) {
-                                acc = __dadd_rn(acc, pend);
-                                pend = px[j * 4];
-                            }
-                        } else if (c != 0) {
-                            replay_chain<ASSOC>(px, ws.zero, 0, cnt_b, new_b, false, acc, pend);
-                        } else {
-                            /* ref_seq chain with CONT rows (or classic order): a and b separately */
-                            const int2 *pi = reinterpret_cast<const int2 *>(base + 8);
-                            for (int j = 0; j < cnt_b; ++j) {
-                                const int2 ix = pi[j * 4];                  /* .x = ia (low word), .y = ib */
-                                const double va = s_pm[ix.x], vb = s_pm[ix.y];
-                                if (ASSOC == SVGT_ASSOC_CLASSIC) {
-                                    acc = __dadd_rn(__dadd_rn(acc, va), vb);
-                                } else {
-                                    const bool nw = (new_b >> j) & 1u;
-                                    const double u = nw ? pend : 0.0;
-                                    const double t0 = nw ? 0.0 : pend;
-                                    acc = __dadd_rn(acc, u);
-                                    pend = __dadd_rn(__dadd_rn(t0, va), vb);
-                                }
-                            }
-                        }
-                    } else {
-                        const double *px = reinterpret_cast<const double *>(base) + c;
-                        replay_chain<ASSOC>(px, ws.zero, 0, cnt_b, new_b, all_new, acc, pend);
-                    }
+                    if (c_phase == 0) replay_frag<ASSOC>(&ws.park[sl_b][0], c, cnt_b, lead_b, s_pm, acc, pend);
+                    else replay_split<ASSOC>(&ws.park[sl_b][0], c, cnt_b, lead_b, acc, pend);
                 }
                 __syncwarp();
                 if (lane < RG) ws.pend[lane].slot_cnt = 0;
                 pending = 0;
-                all_new = true;
                 if (phase_ends) {
                     if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
                     if (c_phase == 0) sum_frag = acc; else sum_split = acc;
