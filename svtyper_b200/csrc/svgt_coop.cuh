@@ -320,11 +320,12 @@ struct FragOut {
  * Continuation rows are resolved HERE, lane-parallel, so that phase B is one add per row:
  * in the sso order (singlesample.py:254-259, :367-378) a fragment's reads are summed into a sub-total
  * first -- sub = ((0 + a1) + b1) + a2 ... over its rows (CONT rows; EXTRA interval rows add nothing) --
- * and the sub-total is added to the site sum when the next fragment starts.  Each fragment's FIRST row
- * gathers the addends of its continuation rows with shuffles, in row order, and parks the finished
- * sub-total; the absorbed rows park 0.0 (x + 0.0 is exact), so phase B just does acc += pend, pend = s
- * for every row.  Only continuation rows at the very start of a chunk (their fragment began in the
- * previous chunk) are left to phase B: `lead` of them update the carried sub-total first.
+ * and the sub-total is added to the site sum when the next fragment starts.  The running sub-total is
+ * folded forward along each fragment's rows with shuffles, in row order, and parked in the fragment's
+ * LAST row of the chunk; its earlier rows park 0.0 (x + 0.0 is exact), so phase B just does
+ * acc += pend, pend = s for every row and a fragment that continues in the next chunk stays pending.
+ * Only continuation rows at the very start of a chunk (their fragment began in the previous chunk) are
+ * left to phase B: `lead` of them update the carried sub-total first.
  */
 template <int ASSOC>
 __device__ __forceinline__ FragOut score_frag_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const Win *wins,
@@ -475,22 +476,31 @@ __device__ __forceinline__ FragOut score_frag_chunk(const SvgtParams &p, const T
     o.lead = 0;
     if (ASSOC == SVGT_ASSOC_SSO && nm != vm) {          /* the chunk has CONT / EXTRA rows (warp-uniform) */
         const unsigned NN = vm & ~nm;                   /* rows that continue a fragment            */
-        o.lead = nm ? __ffs(nm) - 1 : n;
+        o.lead = nm ? __ffs(nm) - 1 : (n < 32 ? n : 32);
         const bool nonnew = (NN >> lane) & 1u;
-        /* a continuation row normally carries no paired-end weight; if one does, gather those too */
-        const bool pe_too = __ballot_sync(full, nonnew && (p_ref != 0.0 || p_alt != 0.0)) != 0u;
-        bool alive = rv && !nonnew;
+        const bool inner = nonnew && lane >= o.lead;    /* continues a fragment that starts in this chunk */
+        /* distance to the fragment's first row in this chunk */
+        const unsigned below = nm & ((1u << lane) - 1u);
+        const int dist = inner ? lane - (31 - __clz(below)) : 0;
+        /* a continuation row normally carries no paired-end weight; if one does, fold those too */
+        const bool pe_too = __ballot_sync(full, inner && (p_ref != 0.0 || p_alt != 0.0)) != 0u;
         for (int k = 1; k < 32; ++k) {
-            alive = alive && (lane + k < 32) && ((NN >> (lane + k < 32 ? lane + k : 31)) & 1u);
-            if (!__any_sync(full, alive)) break;
-            const double ak = __shfl_down_sync(full, va, k), bk = __shfl_down_sync(full, vb, k);
-            if (alive) o.s = __dadd_rn(__dadd_rn(o.s, ak), bk);
+            if (!__any_sync(full, dist >= k)) break;
+            const double up = __shfl_up_sync(full, o.s, 1);
+            if (dist == k) o.s = __dadd_rn(__dadd_rn(up, va), vb);
             if (pe_too) {
-                const double rk = __shfl_down_sync(full, p_ref, k), qk = __shfl_down_sync(full, p_alt, k);
-                if (alive) { o.p_ref = __dadd_rn(o.p_ref, rk); o.p_alt = __dadd_rn(o.p_alt, qk); }
+                const double ur = __shfl_up_sync(full, o.p_ref, 1), ua = __shfl_up_sync(full, o.p_alt, 1);
+                if (dist == k) { o.p_ref = __dadd_rn(ur, p_ref); o.p_alt = __dadd_rn(ua, p_alt); }
             }
         }
-        if (nonnew && lane >= o.lead) { o.s = 0.0; o.p_ref = 0.0; o.p_alt = 0.0; }   /* absorbed by its first row */
+        /* the running sub-total lives in the LAST row of the fragment (within the chunk); earlier rows
+         * park 0.0, so phase B's "acc += pend; pend = s" leaves the sub-total pending, un-flushed, in
+         * case the fragment continues in the next chunk */
+        const bool has_next = lane + 1 < 32 && ((NN >> (lane + 1 < 32 ? lane + 1 : 31)) & 1u);
+        if (lane >= o.lead && has_next) {
+            o.s = 0.0;
+            if (pe_too) { o.p_ref = 0.0; o.p_alt = 0.0; }    /* folded forward above; otherwise every row keeps its own */
+        }
     }
     return o;
 }
@@ -510,6 +520,7 @@ __device__ __forceinline__ void replay_frag(const void *base, int c, int cnt, in
 {
     const double *px = reinterpret_cast<const double *>(base) + (c == 0 ? 0 : c + 1);
     const int2 *pi = reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(base) + 8);   /* .x = ia, .y = ib */
+    lead = lead < cnt ? lead : cnt;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
         /* classic.py:306-311,339-408: every read goes straight into the site sum */
         if (c == 0) {
@@ -576,17 +587,19 @@ __device__ __forceinline__ SplitOut score_split_chunk(const SiteS &S, const doub
     const unsigned nm = __ballot_sync(full, rv && (sfl & S_FIRST));
     if (ASSOC == SVGT_ASSOC_SSO && nm != vm) {
         const unsigned NN = vm & ~nm;
-        o.lead = nm ? __ffs(nm) - 1 : n;
+        o.lead = nm ? __ffs(nm) - 1 : (n < 32 ? n : 32);
         const bool nonnew = (NN >> lane) & 1u;
+        const bool inner = nonnew && lane >= o.lead;
+        const unsigned below = nm & ((1u << lane) - 1u);
+        const int dist = inner ? lane - (31 - __clz(below)) : 0;
         const double vs0 = o.vseq, vc0 = o.vclip;
-        bool alive = rv && !nonnew;
         for (int k = 1; k < 32; ++k) {
-            alive = alive && (lane + k < 32) && ((NN >> (lane + k < 32 ? lane + k : 31)) & 1u);
-            if (!__any_sync(full, alive)) break;
-            const double sk = __shfl_down_sync(full, vs0, k), ck = __shfl_down_sync(full, vc0, k);
-            if (alive) { o.vseq = __dadd_rn(o.vseq, sk); o.vclip = __dadd_rn(o.vclip, ck); }
+            if (!__any_sync(full, dist >= k)) break;
+            const double us = __shfl_up_sync(full, o.vseq, 1), uc = __shfl_up_sync(full, o.vclip, 1);
+            if (dist == k) { o.vseq = __dadd_rn(us, vs0); o.vclip = __dadd_rn(uc, vc0); }
         }
-        if (nonnew && lane >= o.lead) { o.vseq = 0.0; o.vclip = 0.0; }
+        const bool has_next = lane + 1 < 32 && ((NN >> (lane + 1 < 32 ? lane + 1 : 31)) & 1u);
+        if (lane >= o.lead && has_next) { o.vseq = 0.0; o.vclip = 0.0; }
     }
     return o;
 }
@@ -596,6 +609,7 @@ template <int ASSOC>
 __device__ __forceinline__ void replay_split(const void *base, int c, int cnt, int lead, double &acc, double &pend)
 {
     const double *px = reinterpret_cast<const double *>(base) + c;
+    lead = lead < cnt ? lead : cnt;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
 #pragma unroll 4
         for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 4]);
