@@ -200,7 +200,37 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     __syncwarp();
                 }
             };
-#if SVGT_ROWBUFS == 3
+#if SVGT_ROWBUFS == 1
+            /* no register prefetch: the other warps of the SM cover the load */
+            int cs0 = 0, cg0 = 0;
+            bool k0 = advance(cs0, cg0);
+            while (k0) {
+                int4 l0, h0;
+                load_rows(cs0, cg0, l0, h0);
+                int cs1 = 0, cg1 = 0;
+                const bool k1 = advance(cs1, cg1);
+                process(cs0, cg0, l0, h0, !k1 || cs1 != cs0);
+                cs0 = cs1; cg0 = cg1; k0 = k1;
+            }
+#elif SVGT_ROWBUFS == 4
+            /* rotating register queue, three chunks in flight */
+            int cs0 = 0, cg0 = 0, cs1 = 0, cg1 = 0, cs2 = 0, cg2 = 0, cs3 = 0, cg3 = 0;
+            int4 l0, h0, l1, h1, l2, h2, l3, h3;
+            bool k0 = advance(cs0, cg0);
+            if (k0) load_rows(cs0, cg0, l0, h0);
+            bool k1 = k0 && advance(cs1, cg1);
+            if (k1) load_rows(cs1, cg1, l1, h1);
+            bool k2 = k1 && advance(cs2, cg2);
+            if (k2) load_rows(cs2, cg2, l2, h2);
+            while (k0) {
+                const bool k3 = k2 && advance(cs3, cg3);
+                if (k3) load_rows(cs3, cg3, l3, h3);
+                process(cs0, cg0, l0, h0, !k1 || cs1 != cs0);
+                cs0 = cs1; cg0 = cg1; l0 = l1; h0 = h1; k0 = k1;
+                cs1 = cs2; cg1 = cg2; l1 = l2; h1 = h2; k1 = k2;
+                cs2 = cs3; cg2 = cg3; l2 = l3; h2 = h3; k2 = k3;
+            }
+#elif SVGT_ROWBUFS == 3
             /* rotating register queue: while one chunk is scored the next TWO are in flight; the
              * rotation is 16 register moves (FMA pipe, otherwise idle) instead of a third code copy */
             int cs0 = 0, cg0 = 0, cs1 = 0, cg1 = 0, cs2 = 0, cg2 = 0;
@@ -262,6 +292,7 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                     q0 = ldg4(rp); q1 = ldg4(rp + 1);
                 }
             };
+#if SVGT_SPLIT_ROT
             int ss0 = 0, sg0 = 0, ss1 = 0, sg1 = 0, ss2 = 0, sg2 = 0;
             int4 a0, b0, a1, b1, a2, b2;
             bool e0 = advance_split(ss0, sg0);
@@ -292,6 +323,31 @@ __global__ void __launch_bounds__(SVGT_COOP_THREADS, (G >= 8 ? 2 : 3)) svgt_tall
                 ss0 = ss1; sg0 = sg1; a0 = a1; b0 = b1; e0 = e1;
                 ss1 = ss2; sg1 = sg2; a1 = a2; b1 = b2; e1 = e2;
             }
+#else
+            int ss0 = 0, sg0 = 0;
+            bool e0 = advance_split(ss0, sg0);
+            while (e0) {
+                int4 q0, q1;
+                load_split(ss0, sg0, q0, q1);
+                const SiteS &S = ws.site[sg0];
+                const int n = min(32, S.ns - ss0 * 32);
+                const SplitOut so = score_split_chunk<ASSOC>(S, s_pm, lane, n, slop, q0, q1);
+                *reinterpret_cast<double2 *>(&ws.contrib[sg0][lane][0]) = make_double2(so.vseq, so.vclip);
+                if (lane == 0) ws.newmask[sg0] = (unsigned)so.lead;
+                int ss1 = 0, sg1 = 0;
+                const bool e1 = advance_split(ss1, sg1);
+                if (!e1 || ss1 != ss0) {                        /* last chunk of its super-step: phase B */
+                    __syncwarp();
+                    if (gb < G && c < 2) {
+                        int cnt = ws.site[gb].ns - ss0 * 32;
+                        cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+                        replay_split<ASSOC>(&ws.contrib[gb][0][0], c, cnt, (int)ws.newmask[gb], acc, pend);
+                    }
+                    __syncwarp();
+                }
+                ss0 = ss1; sg0 = sg1; e0 = e1;
+            }
+#endif
             if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
             sum_split = acc;
         }

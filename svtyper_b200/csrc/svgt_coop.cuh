@@ -22,6 +22,9 @@ namespace {
 #ifndef SVGT_USE_SAME
 #define SVGT_USE_SAME 1
 #endif
+#ifndef SVGT_SPLIT_ROT
+#define SVGT_SPLIT_ROT 0
+#endif
 #ifndef SVGT_L2_PREFETCH
 #define SVGT_L2_PREFETCH 0
 #endif
