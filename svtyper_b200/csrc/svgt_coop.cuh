@@ -317,6 +317,7 @@ struct FragOut {
     double s, p_ref, p_alt;         /* ref_seq / ref_span / alt_span addends this row parks (see below)     */
     int ia, ib;                     /* prob_mapq LUT indices of the row's own ref_seq addends a, b (0 = none) */
     int lead;                       /* warp-uniform: leading rows that continue the previous chunk's fragment */
+    bool need_idx;                  /* warp-uniform: phase B may read ia / ib of this chunk (lean kernel only)  */
 };
 
 /*
@@ -476,7 +477,7 @@ __device__ __forceinline__ FragOut score_frag_chunk(const SvgtParams &p, const T
     FragOut o;
     o.s = __dadd_rn(va, vb); o.p_ref = p_ref; o.p_alt = p_alt;
     o.ia = hitA ? mqA : 0; o.ib = hitB ? mqB : 0;
-    o.lead = 0;
+    o.lead = 0; o.need_idx = true;
     if (ASSOC == SVGT_ASSOC_SSO && nm != vm) {          /* the chunk has CONT / EXTRA rows (warp-uniform) */
         const unsigned NN = vm & ~nm;                   /* rows that continue a fragment            */
         o.lead = nm ? __ffs(nm) - 1 : (n < 32 ? n : 32);
@@ -523,6 +524,7 @@ __device__ __forceinline__ void replay_frag(const void *base, int c, int cnt, in
 {
     const double *px = reinterpret_cast<const double *>(base) + (c == 0 ? 0 : c + 1);
     const int2 *pi = reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(base) + 8);   /* .x = ia, .y = ib */
+    if (cnt <= 0) return;                               /* no chunk of this site in the super-step: `lead` is stale */
     lead = lead < cnt ? lead : cnt;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
         /* classic.py:306-311,339-408: every read goes straight into the site sum */
@@ -612,6 +614,7 @@ template <int ASSOC>
 __device__ __forceinline__ void replay_split(const void *base, int c, int cnt, int lead, double &acc, double &pend)
 {
     const double *px = reinterpret_cast<const double *>(base) + c;
+    if (cnt <= 0) return;
     lead = lead < cnt ? lead : cnt;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
 #pragma unroll 4

@@ -22,7 +22,8 @@ enum {
     SVGT_VAR_COOP = 2,     /* warp-cooperative, 8 sites interleaved per warp (svgt_coop.cu) */
     SVGT_VAR_COOP4 = 3,    /* warp-cooperative, 4 sites interleaved per warp                 */
     SVGT_VAR_RING = 4,     /* warp-cooperative, rows through a cp.async.bulk smem ring (svgt_ring.cu) */
-    SVGT_VAR_COUNT = 5
+    SVGT_VAR_LEAN = 5,     /* warp-cooperative with the lean row scorer (svgt_lean.cu), the default         */
+    SVGT_VAR_COUNT = 6
 };
 #define SVGT_COOP_THREADS 256       /* 8 warps per CTA in the cooperative kernel     */
 
@@ -52,3 +53,4 @@ size_t svgt_score_smem_bytes(const SvgtParams &p, int variant);
 int svgt_launch_coop(const SvgtParams &p, int variant, cudaStream_t stream);
 int svgt_launch_call(const SvgtParams &p, cudaStream_t stream);
 int svgt_launch_ring(const SvgtParams &p, cudaStream_t stream);
+int svgt_launch_lean(const SvgtParams &p, cudaStream_t stream);

@@ -1,0 +1,378 @@
+/*
+ * svgt_lean.cu -- the default tally kernel (variant 5): the warp-cooperative mapping of svgt_coop.cu
+ * (phase A one evidence row per lane, phase B one ordered fp64 chain per lane; reference
+ * singlesample.py:355-404) with the lean row scorer of svgt_lean.cuh.
+ *
+ * What differs from svgt_tally_kernel (svgt_coop.cu), all of it aimed at the two limits ncu showed
+ * there -- instruction issue and shared-memory wavefronts, not HBM:
+ *   - per site the kernel pre-digests SiteF (two uniform LDS.128 per chunk) and per (site, library)
+ *     WinF (two LDS.128 per row instead of four); non-fast sites (inversions, breakends on two
+ *     contigs, a breakend within min_aligned of the contig start) build the cooperative kernel's
+ *     windows on demand and take its scorer, so every batch is still covered;
+ *   - the insert-size histograms of the first four libraries live in shared memory with a zero
+ *     sentinel behind each, so a look-up is an index clamp; the literal fp64 path reads the
+ *     global copy;
+ *   - a row parks 24 bytes {a + b, p_ref, p_alt} (plus the two LUT indices only when phase B can
+ *     need them), as one STS.64 and one STS.128.
+ * The genotype call is the same second launch (svgt_call_kernel, svgt_coop.cu).
+ */
+#include "svgt_lean.cuh"
+
+namespace {
+
+#ifndef SVGT_LEAN_THREADS
+#define SVGT_LEAN_THREADS 512       /* one CTA of 16 warps per SM: the per-CTA tables are paid once */
+#endif
+#ifndef SVGT_LEAN_MINB
+#define SVGT_LEAN_MINB 1
+#endif
+#ifndef SVGT_LEAN_DEPTH
+#define SVGT_LEAN_DEPTH 3           /* chunks in flight per warp (1 KB each) */
+#endif
+constexpr int kD = SVGT_LEAN_DEPTH;
+constexpr int kLeanWarps = SVGT_LEAN_THREADS / 32;
+constexpr int kHistPad = 8;         /* sentinels behind the cached libraries' counts */
+
+template <int G>
+struct alignas(128) LeanSmem {
+    unsigned char ring[kD][1024];   /* cp.async targets: 32 x 16 B low halves, then 32 x 16 B high halves */
+    SiteS site[G];
+    SiteF sf[G];
+    WinF wf[G][kWLibs + 1];
+    Win gwin[kWLibs];               /* windows of the non-fast site being scored */
+    Parked park[G];                 /* phase A -> phase B */
+    unsigned newmask[G];
+    double zero[2];
+};
+
+__device__ __forceinline__ unsigned lean_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__host__ __device__ __forceinline__ long long lean_hist_words(long long n_hist)
+{
+    return (n_hist < SVGT_SMEM_HIST_WORDS ? n_hist : SVGT_SMEM_HIST_WORDS) + kHistPad;
+}
+
+/* non-fast sites: the cooperative kernel's scorer, out of line so the hot loop stays small; everything
+ * the hot loop keeps in registers travels by value */
+struct GenericOut { FragOut fo; unsigned carryA, carryB; int err; };
+
+#ifndef SVGT_LEAN_GENERIC_INLINE
+#define SVGT_LEAN_GENERIC_INLINE 0
+#endif
+template <int ASSOC>
+#if SVGT_LEAN_GENERIC_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+GenericOut generic_frag_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const Win *wins, const double *s_pm,
+                              const LibK *s_lib, const int lane, const int n, const int g, const int m, const int4 lo,
+                              const int4 hi, unsigned carryA, unsigned carryB, int err)
+{
+    GenericOut r;
+    r.fo = score_frag_chunk<ASSOC>(p, t, S, wins, s_pm, s_lib, p.hist, lane, n, g, m, lo, hi, carryA, carryB, err);
+    r.carryA = carryA; r.carryB = carryB; r.err = err;
+    return r;
+}
+
+template <int G, int ASSOC>
+__global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_kernel(const SvgtParams p)
+{
+    typedef LeanSmem<G> WS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_pm = reinterpret_cast<double *>(smem_raw);
+    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 512);     /* pm[0..255], then pm[q] / 2 */
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
+    LibF *s_libf = reinterpret_cast<LibF *>(smem_raw + off);
+    off += (kWLibs + 1) * sizeof(LibF);
+    off = (off + 127) & ~(size_t)127;
+    WS *s_warp = reinterpret_cast<WS *>(smem_raw + off);
+    off += sizeof(WS) * kLeanWarps;
+    unsigned *s_hist = reinterpret_cast<unsigned *>(smem_raw + off);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    int err = 0;
+    const int nl = p.n_lib < SVGT_SMEM_LIBS ? p.n_lib : SVGT_SMEM_LIBS;
+    for (int i = tid; i < 256; i += SVGT_LEAN_THREADS) {
+        const double v = p.pm[i];
+        s_pm[i] = v;
+        s_pm[256 + i] = __dmul_rn(v, 0.5);
+    }
+    for (int i = tid; i < nl; i += SVGT_LEAN_THREADS) s_lib[i] = derive_lib(p, i, &err);
+    /* the 32-bit form of 19*h1 > h2 needs every histogram count below 2^26 */
+    int big = 0;
+    for (long long i = tid; i < p.n_hist; i += SVGT_LEAN_THREADS) big |= p.hist[i] >= (1u << 26);
+    WS &ws = s_warp[warp];
+    if (lane < 2) ws.zero[lane] = 0.0;
+    if (lane < G) ws.newmask[lane] = 0u;
+    const bool small_counts = __syncthreads_or(big) == 0;
+    /* lean copies of the first kWLibs histograms, each followed by a zero sentinel */
+    if (tid == 0) {
+        const long long cap = lean_hist_words(p.n_hist);
+        long long base = 0;
+        for (int l = 0; l <= kWLibs; ++l) {
+            LibF f; f.addr = 0u; f.len = 0; f.ok = 0; f.pad = 0;
+            if (l < kWLibs && l < nl) {
+                const LibK &L = s_lib[l];
+                const bool fits = L.hist_len < (1 << kHistLenBits) && base + L.hist_len + 1 <= cap;
+                if (L.safe && small_counts && fits) {
+                    f.addr = lean_smem_addr(s_hist + base); f.len = L.hist_len; f.ok = 1;
+                    base += L.hist_len + 1;
+                }
+            }
+            s_libf[l] = f;
+        }
+    }
+    __syncthreads();
+    for (int l = 0; l < kWLibs; ++l) {
+        const LibF f = s_libf[l];
+        if (!f.ok) continue;
+        unsigned *dst = s_hist + ((f.addr - lean_smem_addr(s_hist)) >> 2);
+        const unsigned *src = p.hist + s_lib[l].hist_off;
+        for (int i = tid; i <= f.len; i += SVGT_LEAN_THREADS) dst[i] = i < f.len ? src[i] : 0u;
+    }
+    __syncthreads();
+
+    Tables t;
+    t.pm = s_pm; t.libs = s_lib; t.hist = p.hist;           /* literal paths read the global counts */
+    t.conc = p.consts[C_CONC]; t.disc = p.consts[C_DISC];
+    const int m = p.min_aligned, slop = p.split_slop;
+    const unsigned zero_addr = lean_smem_addr(&ws.zero[0]);
+
+    /* phase-B role of this lane: chain c of interleaved site gb */
+    const int gb = lane >> 2, c = lane & 3;
+    const long long n_units = (p.n_sites + G - 1) / G;
+
+    long long unit = 0, unit_next = 0;
+    if (lane == 0) unit = (long long)atomicAdd(reinterpret_cast<unsigned *>(p.status + 1), 1u);
+    unit = __shfl_sync(full, unit, 0);
+    for (; unit < n_units; unit = __shfl_sync(full, unit_next, 0)) {
+
+        /* ---- lanes 0..G-1 read their site row and publish the scalars ---- */
+        {
+            const long long idx = unit * G + lane;
+            const bool valid = lane < G && idx < p.n_sites;
+            long long site = 0;
+            if (valid) site = p.order ? (long long)p.order[idx] : idx;
+            int4 a = make_int4(0, 0, 0, 0), b = a, cc = a, d = a;
+            if (valid) {
+                const int4 *sp = p.sites + site * 4;
+                a = ldg4(sp); b = ldg4(sp + 1); cc = ldg4(sp + 2); d = ldg4(sp + 3);
+            }
+            const int meta = cc.y;
+            const bool ranged = site_fields_in_range(a, b, m, slop);
+            const bool run = valid && !(meta & SITE_SKIP) && ranged;
+            const long long foff = ((long long)(unsigned)cc.z) | ((long long)cc.w << 32);
+            const long long soff = ((long long)(unsigned)d.y) | ((long long)d.z << 32);
+            int nf = run ? d.x : 0, ns = run ? d.w : 0;
+            if (nf < 0 || foff < 0 || foff + nf > p.n_frag) { nf = 0; err = SVGT_ERR_ARG; }
+            if (ns < 0 || soff < 0 || soff + ns > p.n_split) { ns = 0; err = SVGT_ERR_ARG; }
+            if (lane < G) {
+                SiteS &S = ws.site[lane];
+                S.tA = b.z; S.tB = b.w;
+                S.wA0 = a.x - m; S.wA1 = a.x + m; S.wB0 = a.y - m; S.wB1 = a.y + m;
+                S.meta = (meta & 15) | ((a.x - m >= 0) << 8) | ((a.y - m >= 0) << 9);
+                S.var_length = cc.x;
+                S.posA = a.x; S.posB = a.y; S.ciA0 = a.z; S.ciA1 = a.w; S.ciB0 = b.x; S.ciB1 = b.y;
+                S.dAB = a.y - a.x; S.nf = nf; S.foff = foff; S.soff = soff; S.ns = ns;
+                S.slot = valid ? (int)site : -1;        /* where the sums go (order[] is int32) */
+                SiteF &F = ws.sf[lane];
+                const int svtype = meta & 3;
+                F.tA = b.z; F.wA0 = a.x - m; F.wA1 = a.x + m; F.wB0 = a.y - m; F.wB1 = a.y + m;
+                F.pat = (meta & (SITE_O1_REV | SITE_O2_REV)) | F_PAIRED;   /* site bits 2,3 line up with F_REV_A/B */
+                F.del = svtype == SV_DEL;
+                F.fast = (a.x - m >= 0) && (a.y - m >= 0) && svtype != SV_INV && b.z == b.w;
+            }
+            __syncwarp();
+            for (int i = lane; i < G * (kWLibs + 1); i += 32) {
+                const int g = i / (kWLibs + 1), l = i % (kWLibs + 1);
+                if (ws.site[g].nf && ws.sf[g].fast)
+                    ws.wf[g][l] = make_winf(ws.site[g], s_lib[l < nl ? l : 0], s_libf[l < nl ? l : kWLibs], m, zero_addr);
+            }
+            __syncwarp();
+        }
+
+        /* claim the next unit now: the atomic's round trip is hidden behind this unit's rows */
+        if (lane == 0) unit_next = (long long)atomicAdd(reinterpret_cast<unsigned *>(p.status + 1), 1u);
+
+        double sum_frag = 0.0;      /* lane 4g+c: chain c of the fragment rows of site g */
+        double sum_split = 0.0;     /* lane 4g+c: chain c of the split rows of site g    */
+        {
+            /*
+             * One chunk stream per unit: fragment chunks step-major over the sites that still have rows,
+             * then split chunks the same way (both are 32-byte rows).  A chunk is described by one int,
+             * phase << 27 | step << 3 | g.  Rows travel HBM -> shared memory by cp.async (LDGSTS, 16 bytes
+             * per lane twice, zero-filled beyond the site's last row), kD chunks ahead of the one being
+             * scored; a lane reads back exactly the row it copied, so completion is the lane's own
+             * cp.async.wait_group and no registers or scoreboards are held by rows in flight.
+             */
+            double acc = 0.0, pend = 0.0;
+            unsigned carryA = 0u, carryB = 0u;      /* EXTRA-run hits carried into the next step, bit g */
+            const int my_nf = lane < G ? ws.site[lane].nf : 0;
+            const int my_ns = lane < G ? ws.site[lane].ns : 0;
+            int it_phase = 0, it_step = -1;
+            unsigned it_mask = 0u;
+            auto next_chunk = [&]() -> int {
+                while (it_mask == 0u) {
+                    ++it_step;
+                    it_mask = __ballot_sync(full, (it_phase ? my_ns : my_nf) > it_step * 32);
+                    if (it_mask == 0u) {
+                        if (it_phase) return -1;
+                        it_phase = 1; it_step = -1;
+                    }
+                }
+                const int g = __ffs(it_mask) - 1;
+                it_mask &= it_mask - 1u;
+                return (it_phase << 27) | (it_step << 3) | g;
+            };
+            const unsigned ring = lean_smem_addr(&ws.ring[0][0]) + lane * 16;
+            auto issue = [&](const int d, const unsigned slot) {
+                if (d >= 0) {
+                    const int g = d & 7, step = (d >> 3) & 0xFFFFFF;
+                    const SiteS &S = ws.site[g];
+                    const bool sp = (d >> 27) != 0;
+                    const int n = (sp ? S.ns : S.nf) - step * 32;
+                    const int4 *base = sp ? p.splits : p.frags;
+                    const int4 *src = base;
+                    unsigned bytes = 0u;
+                    if (lane < n) { src = base + 2 * ((sp ? S.soff : S.foff) + (long long)step * 32 + lane); bytes = 16u; }
+                    const unsigned dst = ring + slot * 1024u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 512u), "l"(src + 1), "r"(bytes)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            /* descriptors of the chunk being scored (dq[0]) and of the kD chunks in flight behind it */
+            int dq[kD + 1];
+            unsigned head = 0u;                     /* ring slot of dq[0] */
+#pragma unroll
+            for (int i = 0; i < kD; ++i) {
+                dq[i] = next_chunk();
+                issue(dq[i], (unsigned)i);
+            }
+            while (dq[0] >= 0) {
+                const int d = dq[0];
+                asm volatile("cp.async.wait_group %0;" ::"n"(kD - 1) : "memory");
+                const unsigned src = ring + head * 1024u;
+                int4 lo, hi;
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(src));
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                             : "r"(src + 512u));
+                /* refill the slot just read with the chunk kD ahead */
+                dq[kD] = next_chunk();
+                issue(dq[kD], head);
+                head = head + 1u == (unsigned)kD ? 0u : head + 1u;
+
+                const int g = d & 7, step = (d >> 3) & 0xFFFFFF;
+                const bool sp = (d >> 27) != 0;
+                if (!sp) {
+                    /* ---- phase A, fragment rows ---- */
+                    const int n = ws.site[g].nf - step * 32;
+                    FragOut fo;
+                    if (ws.sf[g].fast) {
+                        fo = score_frag_chunk_fast<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, n, g, m,
+                                                          lo, hi, carryA, carryB, err);
+                    } else {
+                        __syncwarp();
+                        if (lane < kWLibs) {
+                            if (lane < nl) ws.gwin[lane] = make_win(ws.site[g], s_lib[lane], m, small_counts);
+                            else ws.gwin[lane].flags = 0u;
+                        }
+                        __syncwarp();
+                        const GenericOut r = generic_frag_chunk<ASSOC>(p, t, ws.site[g], &ws.gwin[0], s_pm, s_lib, lane, n, g,
+                                                                       m, lo, hi, carryA, carryB, err);
+                        fo = r.fo; carryA = r.carryA; carryB = r.carryB; err = r.err;
+                    }
+                    park_frag_soa<ASSOC>(ws.park[g], lane, fo);
+                    if (lane == 0) ws.newmask[g] = (unsigned)fo.lead;
+                } else {
+                    /* ---- phase A, split rows ---- */
+                    const SiteS &S = ws.site[g];
+                    const int n = min(32, S.ns - step * 32);
+                    const SplitOut so = score_split_chunk<ASSOC>(S, s_pm, lane, n, slop, lo, hi);
+                    ws.park[g].ch[0][lane] = so.vseq; ws.park[g].ch[1][lane] = so.vclip;
+                    if (lane == 0) ws.newmask[g] = (unsigned)so.lead;
+                }
+                /* ---- phase B after the last chunk of a super-step (same phase and step) ---- */
+                if ((dq[1] >> 3) != (d >> 3)) {
+                    __syncwarp();
+                    if (gb < G && c < (sp ? 2 : 3)) {
+                        int cnt = (sp ? ws.site[gb].ns : ws.site[gb].nf) - step * 32;
+                        cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+                        if (!sp) replay_frag_soa<ASSOC>(ws.park[gb], c, cnt, (int)ws.newmask[gb], s_pm, acc, pend);
+                        else replay_split_soa<ASSOC>(ws.park[gb], c, cnt, (int)ws.newmask[gb], acc, pend);
+                    }
+                    __syncwarp();
+                    if (!sp && (dq[1] < 0 || (dq[1] >> 27) != 0)) {     /* the fragment rows are done */
+                        if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+                        sum_frag = acc; acc = 0.0; pend = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kD; ++i) dq[i] = dq[i + 1];
+            }
+            if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+            sum_split = acc;
+        }
+
+        /* ---- park the five sums in the site's output row (lane 4g+c holds chain c of site g) ---- */
+        if (gb < G && c < 3) {
+            const int site = ws.site[gb].slot;
+            if (site >= 0 && (ws.site[gb].nf | ws.site[gb].ns)) {
+                double *row = reinterpret_cast<double *>(p.out + site);
+                /* ParkedSums: ref_seq, alt_seq, alt_clip, ref_span, alt_span */
+                if (c == 0) { row[0] = sum_frag; row[1] = sum_split; }
+                else if (c == 1) { row[3] = sum_frag; row[2] = sum_split; }
+                else row[4] = sum_frag;
+            }
+        }
+        __syncwarp();
+    }
+    if (err) {
+        atomicCAS(p.status, 0, err);
+        atomicAdd(p.status + 2, 1);
+    }
+}
+
+template <int G>
+size_t lean_smem_bytes(const SvgtParams &p)
+{
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF);
+    off = (off + 127) & ~(size_t)127;
+    off += sizeof(LeanSmem<G>) * kLeanWarps;
+    off += (size_t)lean_hist_words(p.n_hist) * sizeof(unsigned);
+    return off;
+}
+
+template <int G>
+int launch_lean(const SvgtParams &p, cudaStream_t stream)
+{
+    auto kern = (p.assoc_mode == SVGT_ASSOC_CLASSIC) ? svgt_lean_kernel<G, SVGT_ASSOC_CLASSIC>
+                                                     : svgt_lean_kernel<G, SVGT_ASSOC_SSO>;
+    const size_t smem = lean_smem_bytes<G>(p);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SVGT_LEAN_THREADS, smem)) != cudaSuccess)
+        return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const long long units = (p.n_sites + G - 1) / G;
+    const long long want = (units + kLeanWarps - 1) / kLeanWarps;
+    const long long cap = (long long)sms * per_sm;      /* persistent: one resident wave */
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, SVGT_LEAN_THREADS, smem, stream>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    return svgt_launch_call(p, stream);
+}
+
+}  // namespace
+
+#ifndef SVGT_LEAN_G
+#define SVGT_LEAN_G 8
+#endif
+int svgt_launch_lean(const SvgtParams &p, cudaStream_t stream) { return launch_lean<SVGT_LEAN_G>(p, stream); }

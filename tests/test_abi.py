@@ -65,7 +65,8 @@ def test_set_variant(lib):
     assert lib.svgt_set_variant(2) == 2
     assert lib.svgt_set_variant(3) == 3
     assert lib.svgt_set_variant(4) == 4
-    assert lib.svgt_set_variant(-1) in (0, 1, 2, 3, 4)
+    assert lib.svgt_set_variant(5) == 5
+    assert lib.svgt_set_variant(-1) in (0, 1, 2, 3, 4, 5)
 
 
 def test_no_cpu_fallback(lib):
