@@ -32,12 +32,18 @@ namespace {
 constexpr int kD = SVGT_LEAN_DEPTH;
 constexpr int kLeanWarps = SVGT_LEAN_THREADS / 32;
 constexpr int kHistPad = 8;         /* sentinels behind the cached libraries' counts */
+constexpr int kLeanHistWords = 5120;/* shared-memory budget for the cached counts (the CTA uses ~211 KB besides) */
+
+/* one row stream of a site: where its rows start and how many there are (one uniform LDS.128 per chunk) */
+struct alignas(16) Strm { const int4 *rows; int n; int pad; };
 
 template <int G>
 struct alignas(128) LeanSmem {
     unsigned char ring[kD][1024];   /* cp.async targets: 32 x 16 B low halves, then 32 x 16 B high halves */
+    Strm strm[2][8];                /* row streams: [0] fragment rows, [1] split rows (a chunk's low 4 bits index it) */
     SiteS site[G];
     SiteF sf[G];
+    SplitF spf[G];
     WinF wf[G][kWLibs + 1];
     Win gwin[kWLibs];               /* windows of the non-fast site being scored */
     Parked park[G];                 /* phase A -> phase B */
@@ -49,7 +55,7 @@ __device__ __forceinline__ unsigned lean_smem_addr(const void *p) { return (unsi
 
 __host__ __device__ __forceinline__ long long lean_hist_words(long long n_hist)
 {
-    return (n_hist < SVGT_SMEM_HIST_WORDS ? n_hist : SVGT_SMEM_HIST_WORDS) + kHistPad;
+    return (n_hist < kLeanHistWords ? n_hist : kLeanHistWords) + kHistPad;
 }
 
 /* non-fast sites: the cooperative kernel's scorer, out of line so the hot loop stays small; everything
@@ -183,6 +189,11 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 F.pat = (meta & (SITE_O1_REV | SITE_O2_REV)) | F_PAIRED;   /* site bits 2,3 line up with F_REV_A/B */
                 F.del = svtype == SV_DEL;
                 F.fast = (a.x - m >= 0) && (a.y - m >= 0) && svtype != SV_INV && b.z == b.w;
+                ws.spf[lane] = make_splitf(S, slop);
+                Strm q;
+                q.pad = 0;
+                q.rows = p.frags + 2 * foff; q.n = nf; ws.strm[0][lane] = q;
+                q.rows = p.splits + 2 * soff; q.n = ns; ws.strm[1][lane] = q;
             }
             __syncwarp();
             for (int i = lane; i < G * (kWLibs + 1); i += 32) {
@@ -211,6 +222,7 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
             unsigned carryA = 0u, carryB = 0u;      /* EXTRA-run hits carried into the next step, bit g */
             const int my_nf = lane < G ? ws.site[lane].nf : 0;
             const int my_ns = lane < G ? ws.site[lane].ns : 0;
+            /* a chunk is one int: step << 4 | phase << 3 | g  (its low four bits index ws.strm) */
             int it_phase = 0, it_step = -1;
             unsigned it_mask = 0u;
             auto next_chunk = [&]() -> int {
@@ -219,24 +231,22 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                     it_mask = __ballot_sync(full, (it_phase ? my_ns : my_nf) > it_step * 32);
                     if (it_mask == 0u) {
                         if (it_phase) return -1;
-                        it_phase = 1; it_step = -1;
+                        it_phase = 8; it_step = -1;
                     }
                 }
                 const int g = __ffs(it_mask) - 1;
                 it_mask &= it_mask - 1u;
-                return (it_phase << 27) | (it_step << 3) | g;
+                return (it_step << 4) | it_phase | g;
             };
             const unsigned ring = lean_smem_addr(&ws.ring[0][0]) + lane * 16;
+            const Strm *strm = &ws.strm[0][0];
             auto issue = [&](const int d, const unsigned slot) {
                 if (d >= 0) {
-                    const int g = d & 7, step = (d >> 3) & 0xFFFFFF;
-                    const SiteS &S = ws.site[g];
-                    const bool sp = (d >> 27) != 0;
-                    const int n = (sp ? S.ns : S.nf) - step * 32;
-                    const int4 *base = sp ? p.splits : p.frags;
-                    const int4 *src = base;
-                    unsigned bytes = 0u;
-                    if (lane < n) { src = base + 2 * ((sp ? S.soff : S.foff) + (long long)step * 32 + lane); bytes = 16u; }
+                    const Strm q = strm[d & 15];
+                    const int row = (d >> 4) * 32 + lane;
+                    /* rows beyond the last one are zero-filled (0 source bytes); the address stays in range */
+                    const int4 *src = q.rows + 2 * (long long)min(row, q.n - 1);
+                    const unsigned bytes = row < q.n ? 16u : 0u;
                     const unsigned dst = ring + slot * 1024u;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 512u), "l"(src + 1), "r"(bytes)
@@ -265,15 +275,14 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 issue(dq[kD], head);
                 head = head + 1u == (unsigned)kD ? 0u : head + 1u;
 
-                const int g = d & 7, step = (d >> 3) & 0xFFFFFF;
-                const bool sp = (d >> 27) != 0;
+                const int g = d & 7, step = d >> 4;
+                const bool sp = (d & 8) != 0;
                 if (!sp) {
                     /* ---- phase A, fragment rows ---- */
-                    const int n = ws.site[g].nf - step * 32;
                     FragOut fo;
                     if (ws.sf[g].fast) {
-                        fo = score_frag_chunk_fast<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, n, g, m,
-                                                          lo, hi, carryA, carryB, err);
+                        fo = score_frag_chunk_fast<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, step, g,
+                                                          m, lo, hi, carryA, carryB, err);
                     } else {
                         __syncwarp();
                         if (lane < kWLibs) {
@@ -281,17 +290,16 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                             else ws.gwin[lane].flags = 0u;
                         }
                         __syncwarp();
-                        const GenericOut r = generic_frag_chunk<ASSOC>(p, t, ws.site[g], &ws.gwin[0], s_pm, s_lib, lane, n, g,
-                                                                       m, lo, hi, carryA, carryB, err);
+                        const GenericOut r = generic_frag_chunk<ASSOC>(p, t, ws.site[g], &ws.gwin[0], s_pm, s_lib, lane,
+                                                                       ws.site[g].nf - step * 32, g, m, lo, hi, carryA, carryB,
+                                                                       err);
                         fo = r.fo; carryA = r.carryA; carryB = r.carryB; err = r.err;
                     }
                     park_frag_soa<ASSOC>(ws.park[g], lane, fo);
                     if (lane == 0) ws.newmask[g] = (unsigned)fo.lead;
                 } else {
                     /* ---- phase A, split rows ---- */
-                    const SiteS &S = ws.site[g];
-                    const int n = min(32, S.ns - step * 32);
-                    const SplitOut so = score_split_chunk<ASSOC>(S, s_pm, lane, n, slop, lo, hi);
+                    const SplitOut so = score_split_chunk_lean<ASSOC>(ws.spf[g], s_pm, lane, ws.strm[1][g].n - step * 32, lo, hi);
                     ws.park[g].ch[0][lane] = so.vseq; ws.park[g].ch[1][lane] = so.vclip;
                     if (lane == 0) ws.newmask[g] = (unsigned)so.lead;
                 }
@@ -299,13 +307,13 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 if ((dq[1] >> 3) != (d >> 3)) {
                     __syncwarp();
                     if (gb < G && c < (sp ? 2 : 3)) {
-                        int cnt = (sp ? ws.site[gb].ns : ws.site[gb].nf) - step * 32;
+                        int cnt = ws.strm[sp ? 1 : 0][gb].n - step * 32;
                         cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
                         if (!sp) replay_frag_soa<ASSOC>(ws.park[gb], c, cnt, (int)ws.newmask[gb], s_pm, acc, pend);
                         else replay_split_soa<ASSOC>(ws.park[gb], c, cnt, (int)ws.newmask[gb], acc, pend);
                     }
                     __syncwarp();
-                    if (!sp && (dq[1] < 0 || (dq[1] >> 27) != 0)) {     /* the fragment rows are done */
+                    if (!sp && (dq[1] < 0 || (dq[1] & 8) != 0)) {       /* the fragment rows are done */
                         if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
                         sum_frag = acc; acc = 0.0; pend = 0.0;
                     }

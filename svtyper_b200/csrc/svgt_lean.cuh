@@ -84,12 +84,12 @@ __device__ __forceinline__ WinF make_winf(const SiteS &S, const LibK &L, const L
  *   weights singlesample.py:305-318, :336-350
  */
 __device__ __forceinline__ void fast_row(const int4 lo, const int4 hi, const int4 f0, const int4 f1, const uint4 w0,
-                                         const uint4 w1, unsigned &hAhi, unsigned &hBhi, unsigned &wref,
-                                         unsigned &walt, int &tie)
+                                         const uint4 w1, double &hA, double &hB, double &wref, double &walt, int &tie)
 {
     asm("{\n\t"
         ".reg .pred e1, e2, pfa, pfb, p, q, hA, hB, pe0, pa, pr0, ra, rb, pc, pt, pdel, both, any, x1, ron, aon, ptrap;\n\t"
-        ".reg .b32 t, d, x, o, k2, len, hb, i1, i2, a1, a2, h1, h2, l19;\n\t"
+        ".reg .b32 t, d, x, o, k2, len, hb, i1, i2, a1, a2, h1, h2, l19, zr;\n\t"
+        "mov.b32 zr, 0;\n\t"
         /* tids and presence flags */
         "setp.eq.s32 e1, %9, %12;\n\t"
         "setp.eq.s32 e2, %10, %12;\n\t"
@@ -108,8 +108,10 @@ __device__ __forceinline__ void fast_row(const int4 lo, const int4 hi, const int
         "setp.le.and.s32 q, %7, %15, pfb;\n\t"
         "setp.ge.and.s32 q, %8, %16, q;\n\t"
         "or.pred hB, p, q;\n\t"
-        "selp.b32 %0, 0x3FF00000, 0, hA;\n\t"
-        "selp.b32 %1, 0x3FF00000, 0, hB;\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hA;\n\t"
+        "mov.b64 %0, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hB;\n\t"
+        "mov.b64 %1, {zr, t};\n\t"
         /* paired-end straddles */
         "and.pred pe0, e1, e2;\n\t"
         "and.b32 t, %11, 0x5C;\n\t"
@@ -158,10 +160,12 @@ __device__ __forceinline__ void fast_row(const int4 lo, const int4 hi, const int
         "and.pred x1, pdel, pc;\n\t"
         "and.pred aon, pa, !x1;\n\t"
         "selp.b32 t, 0x3FF00000, 0x3FE00000, both;\n\t"
-        "selp.b32 %2, t, 0, ron;\n\t"
-        "selp.b32 %3, 0x3FF00000, 0, aon;\n\t"
+        "selp.b32 t, t, 0, ron;\n\t"
+        "mov.b64 %2, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, aon;\n\t"
+        "mov.b64 %3, {zr, t};\n\t"
         "}"
-        : "=r"(hAhi), "=r"(hBhi), "=r"(wref), "=r"(walt), "=r"(tie)
+        : "=d"(hA), "=d"(hB), "=d"(wref), "=d"(walt), "=r"(tie)
         : "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.w),          /* %5..%11  */
           "r"(f0.x), "r"(f0.y), "r"(f0.z), "r"(f0.w), "r"(f1.x), "r"(f1.y), "r"(f1.z),          /* %12..%18 */
           "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w) /* %19..%26 */);
@@ -245,18 +249,18 @@ __device__ __noinline__ FoldOut fold_continuations(const int lane, const int n, 
     return o;
 }
 
-/* one 32-row fragment chunk of a FAST site (phase A) */
+/* one 32-row fragment chunk of a FAST site (phase A); rows beyond the site's last one were zero-filled */
 template <int ASSOC>
 __device__ __forceinline__ FragOut score_frag_chunk_fast(const SvgtParams &p, const Tables &t, const SiteS &S,
                                                          const SiteF &F, const WinF *wf, const double *s_pm,
-                                                         const LibK *s_lib, const int lane, const int n, const int g,
+                                                         const LibK *s_lib, const int lane, const int step, const int g,
                                                          const int m, const int4 lo, const int4 hi, unsigned &carryA,
                                                          unsigned &carryB, int &err)
 {
     const unsigned full = 0xffffffffu;
     const int4 f0 = *reinterpret_cast<const int4 *>(&F.tA);
     const int4 f1 = *reinterpret_cast<const int4 *>(&F.wB1);
-    const int fl = hi.w;                                        /* rows beyond n were loaded as zeros */
+    const int fl = hi.w;
     const unsigned z = (unsigned)hi.z;
     const unsigned mqA = z & 0xFFu, mqB = (z >> 8) & 0xFFu;
     const unsigned lib = min(z >> 16, (unsigned)kWLibs);
@@ -264,50 +268,126 @@ __device__ __forceinline__ FragOut score_frag_chunk_fast(const SvgtParams &p, co
     const uint4 w1 = *reinterpret_cast<const uint4 *>(&wf[lib].FL);
     const double pmA = s_pm[mqA], pmB = s_pm[mqB];
 
-    unsigned hAhi, hBhi, wref, walt;
+    double hA, hB, wref, walt;                      /* {0,1}, {0,1}, {0,.5,1}, {0,1} */
     int tie;
-    fast_row(lo, hi, f0, f1, w0, w1, hAhi, hBhi, wref, walt, tie);
+    fast_row(lo, hi, f0, f1, w0, w1, hA, hB, wref, walt, tie);
 
-    /* EXTRA / MULTI / CONT rows (evidence.py) and carried EXTRA hits: out of line, rare */
+    /* one vote for everything rare: EXTRA / MULTI / CONT rows (evidence.py), a p_concordant tie or a
+     * library the integer rewrites do not cover; carried EXTRA hits re-enter through the carry bits */
     unsigned vm = 0u, nm = 0u;
     bool special = false;                                       /* the chunk has CONT / EXTRA rows (warp-uniform) */
-    const unsigned XM = __ballot_sync(full, (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B | F_CONT)) != 0);
-    if (XM != 0u || ((carryA | carryB) >> g) & 1u) {
-        const MultiOut r = resolve_multi(fl, lane, n, g, hAhi, hBhi, carryA, carryB);
-        hAhi = r.hAhi; hBhi = r.hBhi; carryA = r.carryA; carryB = r.carryB; nm = r.nm; vm = r.vm;
-        special = nm != vm;
-    }
-
-    /* p_concordant tie, or a library the integer rewrites do not cover: the literal row */
-    if (__any_sync(full, tie != 0)) {
-        if (tie != 0 && (fl & (F_PAIRED | F_EXTRA)) == F_PAIRED) {
+    const bool xrow = (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B | F_CONT)) != 0;
+    if (__any_sync(full, xrow || tie != 0) || (((carryA | carryB) >> g) & 1u)) {
+        if (__any_sync(full, xrow) || (((carryA | carryB) >> g) & 1u)) {
+            const MultiOut r = resolve_multi(fl, lane, S.nf - step * 32, g, (unsigned)__double2hiint(hA),
+                                             (unsigned)__double2hiint(hB), carryA, carryB);
+            hA = __hiloint2double((int)r.hAhi, 0); hB = __hiloint2double((int)r.hBhi, 0);
+            carryA = r.carryA; carryB = r.carryB; nm = r.nm; vm = r.vm;
+            special = nm != vm;
+        }
+        if (tie != 0 && (fl & (F_PAIRED | F_EXTRA)) == F_PAIRED) {      /* the literal row */
             bool alt, refA, refB, pc;
             slow_row(p, t, S, lo, hi, s_lib, m, err, alt, refA, refB, pc);
             const bool is_del = F.del != 0;
             const bool both = refA & refB;
             const bool ref_on = (refA | refB) & (!both | is_del) & pc;
             const bool alt_on = alt & !(is_del & pc);
-            wref = ref_on ? (both ? kOneHi : kHalfHi) : 0u;
-            walt = alt_on ? kOneHi : 0u;
+            wref = ref_on ? (both ? 1.0 : 0.5) : 0.0;
+            walt = alt_on ? 1.0 : 0.0;
         }
     }
 
     /* singlesample.py:254-259: a = pm[A] if read A covers a breakend; :305-350: p_alt, p_ref */
     const double prod = __dmul_rn(pmA, pmB);
-    const double p_ref = __dmul_rn(prod, __hiloint2double((int)wref, 0));
-    const double p_alt = __dmul_rn(prod, __hiloint2double((int)walt, 0));
-    const double hA = __hiloint2double((int)hAhi, 0);
-    const double vb = __dmul_rn(pmB, __hiloint2double((int)hBhi, 0));
+    const double vb = __dmul_rn(pmB, hB);
     FragOut o;
     o.s = __fma_rn(pmA, hA, vb);                       /* pmA * {0,1} is exact: one rounding, a + b */
-    o.p_ref = p_ref; o.p_alt = p_alt;
-    o.ia = 0; o.ib = 0;
-    o.lead = 0;
-    o.need_idx = (ASSOC == SVGT_ASSOC_CLASSIC) || special;      /* phase B reads ia / ib only then */
-    if (o.need_idx) { o.ia = hAhi ? (int)mqA : 0; o.ib = hBhi ? (int)mqB : 0; }
-    if (ASSOC == SVGT_ASSOC_SSO && special) {
-        const FoldOut r = fold_continuations(lane, n, nm, vm, __dmul_rn(pmA, hA), vb, o.s, p_ref, p_alt);
+    o.p_ref = __dmul_rn(prod, wref); o.p_alt = __dmul_rn(prod, walt);
+    o.ia = 0; o.ib = 0; o.lead = 0; o.need_idx = false;
+    if (ASSOC == SVGT_ASSOC_CLASSIC) {                  /* phase B adds a and b one by one: park their LUT indices */
+        o.ia = hA != 0.0 ? (int)mqA : 0; o.ib = hB != 0.0 ? (int)mqB : 0;
+    } else if (special) {
+        const FoldOut r = fold_continuations(lane, S.nf - step * 32, nm, vm, __dmul_rn(pmA, hA), vb, o.s, o.p_ref, o.p_alt);
         o.s = r.s; o.p_ref = r.p_ref; o.p_alt = r.p_alt; o.lead = r.lead;
+        if (lane < r.lead) { o.ia = hA != 0.0 ? (int)mqA : 0; o.ib = hB != 0.0 ? (int)mqB : 0; }
+    }
+    return o;
+}
+
+/* ---- split rows of any site (parsers.py:1122-1215, singlesample.py:262-274), pre-digested per site ---- */
+struct SplitF {
+    int tL, tR, loL, loR;        /* breakends left to right (parsers.py:1143-1161); lo = pos - slop */
+    int w1, rL, rR, kind;        /* w1 = 2 * slop + 1; kind of a SOFT-CLIPPED row: 0 as a plain one (DEL), 1 DUP, 2 INV, 3 none */
+};
+
+__device__ __forceinline__ SplitF make_splitf(const SiteS &S, int slop)
+{
+    SplitF f;
+    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
+    const bool swap = (S.tA != S.tB) || (S.posA > S.posB);
+    f.tL = swap ? S.tB : S.tA; f.tR = swap ? S.tA : S.tB;
+    f.loL = (swap ? S.posB : S.posA) - slop; f.loR = (swap ? S.posA : S.posB) - slop;
+    f.w1 = 2 * slop + 1;
+    f.rL = swap ? o2 : o1; f.rR = swap ? o1 : o2;
+    f.kind = svtype == SV_DEL ? 0 : svtype == SV_DUP ? 1 : svtype == SV_INV ? 2 : 3;
+    return f;
+}
+
+/* splits that are not the FIRST of their fragment are folded into the first one's sub-totals, as in
+ * score_split_chunk(); .p_ref / .p_alt of the result carry alt_seq / alt_clip */
+__device__ __noinline__ FoldOut fold_splits(const int lane, const int n, const unsigned nm, const double vs0,
+                                            const double vc0)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
+    FoldOut o;
+    o.s = 0.0; o.p_ref = vs0; o.p_alt = vc0;
+    const unsigned NN = vm & ~nm;
+    o.lead = nm ? __ffs(nm) - 1 : (n < 32 ? n : 32);
+    const bool nonnew = (NN >> lane) & 1u;
+    const bool inner = nonnew && lane >= o.lead;
+    const unsigned below = nm & ((1u << lane) - 1u);
+    const int dist = inner ? lane - (31 - __clz(below)) : 0;
+    for (int k = 1; k < 32; ++k) {
+        if (!__any_sync(full, dist >= k)) break;
+        const double us = __shfl_up_sync(full, o.p_ref, 1), uc = __shfl_up_sync(full, o.p_alt, 1);
+        if (dist == k) { o.p_ref = __dadd_rn(us, vs0); o.p_alt = __dadd_rn(uc, vc0); }
+    }
+    const bool has_next = lane + 1 < 32 && ((NN >> (lane + 1 < 32 ? lane + 1 : 31)) & 1u);
+    if (lane >= o.lead && has_next) { o.p_ref = 0.0; o.p_alt = 0.0; }
+    return o;
+}
+
+/* one 32-row split chunk: parks {alt_seq, alt_clip} addends; same arithmetic as score_split_chunk() */
+template <int ASSOC>
+__device__ __forceinline__ SplitOut score_split_chunk_lean(const SplitF &F, const double *s_pm, const int lane, const int n,
+                                                           const int4 q0, const int4 q1)
+{
+    const unsigned full = 0xffffffffu;
+    const int4 f0 = *reinterpret_cast<const int4 *>(&F.tL);
+    const int4 f1 = *reinterpret_cast<const int4 *>(&F.w1);
+    const bool rv = lane < n;
+    const unsigned z = (unsigned)q1.z;
+    const bool soft = (z >> 16) & S_SOFT_CLIP;
+    const bool first = (z >> 16) & S_FIRST;
+    const unsigned w1 = (unsigned)f1.x;
+    const int cl = f1.y ? q0.y : q0.z, cr = f1.z ? q0.y : q0.z;       /* left piece vs L / R side */
+    const int dl = f1.y ? q1.x : q1.y, dr = f1.z ? q1.x : q1.y;       /* right piece vs L / R side */
+    const bool lL = (q0.x == f0.x) & ((unsigned)(cl - f0.z) < w1);
+    const bool lR = (q0.x == f0.y) & ((unsigned)(cr - f0.w) < w1);
+    const bool rLs = (q0.w == f0.x) & ((unsigned)(dl - f0.z) < w1);
+    const bool rRs = (q0.w == f0.y) & ((unsigned)(dr - f0.w) < w1);
+    const int kind = soft ? f1.w : 0;
+    const bool Ls = rv & (kind == 0 ? lL : kind == 1 ? lR : kind == 2 ? (lL | lR) : false);
+    const bool Rs = rv & (kind == 0 ? rRs : kind == 1 ? rLs : kind == 2 ? (rLs | rRs) : false);
+    const double x = s_pm[Ls ? (z & 0xFFu) : 0u];
+    const double y = s_pm[Rs ? ((z >> 8) & 0xFFu) : 0u];
+    const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);       /* (.. + ..) / 2.0, exact either way */
+    SplitOut o;
+    o.vseq = soft ? 0.0 : p_alt; o.vclip = soft ? p_alt : 0.0; o.lead = 0;
+    if (ASSOC == SVGT_ASSOC_SSO && __any_sync(full, rv && !first)) {     /* extra splits of one fragment: rare */
+        const FoldOut r = fold_splits(lane, n, __ballot_sync(full, rv && first), o.vseq, o.vclip);
+        o.vseq = r.p_ref; o.vclip = r.p_alt; o.lead = r.lead;
     }
     return o;
 }
@@ -325,8 +405,11 @@ struct alignas(8) Parked { double ch[3][33]; };
 template <int ASSOC>
 __device__ __forceinline__ void park_frag_soa(Parked &P, int lane, const FragOut &o)
 {
-    const bool as_idx = (ASSOC == SVGT_ASSOC_CLASSIC) || lane < o.lead;
-    P.ch[0][lane] = as_idx ? __hiloint2double(o.ib, o.ia) : o.s;
+    if (ASSOC == SVGT_ASSOC_CLASSIC) P.ch[0][lane] = __hiloint2double(o.ib, o.ia);
+    else {
+        P.ch[0][lane] = o.s;
+        if (o.lead > 0) { if (lane < o.lead) P.ch[0][lane] = __hiloint2double(o.ib, o.ia); }   /* warp-uniform, rare */
+    }
     P.ch[1][lane] = o.p_ref; P.ch[2][lane] = o.p_alt;
 }
 
@@ -359,7 +442,7 @@ __device__ __forceinline__ void replay_frag_soa(const Parked &P, int c, int cnt,
                 pend = __dadd_rn(pend, px[j]);
             }
         }
-#pragma unroll 4
+#pragma unroll 8
         for (int j = lead; j < cnt; ++j) {
             acc = __dadd_rn(acc, pend);
             pend = px[j];
@@ -379,7 +462,7 @@ __device__ __forceinline__ void replay_split_soa(const Parked &P, int c, int cnt
         for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j]);
     } else {
         for (int j = 0; j < lead; ++j) pend = __dadd_rn(pend, px[j]);
-#pragma unroll 4
+#pragma unroll 8
         for (int j = lead; j < cnt; ++j) {
             acc = __dadd_rn(acc, pend);
             pend = px[j];

@@ -118,7 +118,7 @@ def test_many_libraries_and_large_histogram(eng, oracle):
     big = ev.LibraryTable([synth.gaussian_library(4000, 900)])
     assert big.hist.size > 6144
     b = synth.generate("del10k", n_sites=2000, seed=10, libs=big)
-    for v in (0, 1, 2, 3, 4):
+    for v in (0, 1, 2, 3, 4, 5):
         assert_rows_match(gpu_rows(eng, b, v), oracle.score(b), exact_gl=True, where="big hist")
 
 
