@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
     for (long long i = tid; i < p.n_hist; i += SVGT_LEAN_THREADS) big |= p.hist[i] >= (1u << 26);
     WS &ws = s_warp[warp];
     if (lane < 2) ws.zero[lane] = 0.0;
-    if (lane < G) ws.newmask[lane] = 0u;
     const bool small_counts = __syncthreads_or(big) == 0;
     /* lean copies of the first kWLibs histograms, each followed by a zero sentinel */
     if (tid == 0) {
@@ -220,6 +219,7 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
              */
             double acc = 0.0, pend = 0.0;
             unsigned carryA = 0u, carryB = 0u;      /* EXTRA-run hits carried into the next step, bit g */
+            unsigned long long leads = 0ull;        /* `lead` of each site's chunk in this super-step, 8 bits per site */
             const int my_nf = lane < G ? ws.site[lane].nf : 0;
             const int my_ns = lane < G ? ws.site[lane].ns : 0;
             /* a chunk is one int: step << 4 | phase << 3 | g  (its low four bits index ws.strm) */
@@ -296,12 +296,12 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                         fo = r.fo; carryA = r.carryA; carryB = r.carryB; err = r.err;
                     }
                     park_frag_soa<ASSOC>(ws.park[g], lane, fo);
-                    if (lane == 0) ws.newmask[g] = (unsigned)fo.lead;
+                    if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
                 } else {
                     /* ---- phase A, split rows ---- */
                     const SplitOut so = score_split_chunk_lean<ASSOC>(ws.spf[g], s_pm, lane, ws.strm[1][g].n - step * 32, lo, hi);
                     ws.park[g].ch[0][lane] = so.vseq; ws.park[g].ch[1][lane] = so.vclip;
-                    if (lane == 0) ws.newmask[g] = (unsigned)so.lead;
+                    if (so.lead) leads |= (unsigned long long)so.lead << (8 * g);
                 }
                 /* ---- phase B after the last chunk of a super-step (same phase and step) ---- */
                 if ((dq[1] >> 3) != (d >> 3)) {
@@ -309,9 +309,11 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                     if (gb < G && c < (sp ? 2 : 3)) {
                         int cnt = ws.strm[sp ? 1 : 0][gb].n - step * 32;
                         cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
-                        if (!sp) replay_frag_soa<ASSOC>(ws.park[gb], c, cnt, (int)ws.newmask[gb], s_pm, acc, pend);
-                        else replay_split_soa<ASSOC>(ws.park[gb], c, cnt, (int)ws.newmask[gb], acc, pend);
+                        const int lead = (int)(leads >> (8 * gb)) & 0xFF;
+                        if (!sp) replay_frag_soa<ASSOC>(ws.park[gb], c, cnt, lead, s_pm, acc, pend);
+                        else replay_split_soa<ASSOC>(ws.park[gb], c, cnt, lead, acc, pend);
                     }
+                    leads = 0ull;
                     __syncwarp();
                     if (!sp && (dq[1] < 0 || (dq[1] & 8) != 0)) {       /* the fragment rows are done */
                         if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);

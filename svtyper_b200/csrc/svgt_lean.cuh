@@ -262,11 +262,13 @@ __device__ __forceinline__ FragOut score_frag_chunk_fast(const SvgtParams &p, co
     const int4 f1 = *reinterpret_cast<const int4 *>(&F.wB1);
     const int fl = hi.w;
     const unsigned z = (unsigned)hi.z;
-    const unsigned mqA = z & 0xFFu, mqB = (z >> 8) & 0xFFu;
     const unsigned lib = min(z >> 16, (unsigned)kWLibs);
     const uint4 w0 = *reinterpret_cast<const uint4 *>(&wf[lib].altA_lo);
     const uint4 w1 = *reinterpret_cast<const uint4 *>(&wf[lib].FL);
-    const double pmA = s_pm[mqA], pmB = s_pm[mqB];
+    /* prob_mapq of both reads: byte offsets (mapq * 8) straight out of the packed word */
+    const char *pmb = reinterpret_cast<const char *>(s_pm);
+    const double pmA = *reinterpret_cast<const double *>(pmb + ((z << 3) & 0x7F8u));
+    const double pmB = *reinterpret_cast<const double *>(pmb + ((z >> 5) & 0x7F8u));
 
     double hA, hB, wref, walt;                      /* {0,1}, {0,1}, {0,.5,1}, {0,1} */
     int tie;
@@ -277,12 +279,17 @@ __device__ __forceinline__ FragOut score_frag_chunk_fast(const SvgtParams &p, co
     unsigned vm = 0u, nm = 0u;
     bool special = false;                                       /* the chunk has CONT / EXTRA rows (warp-uniform) */
     const bool xrow = (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B | F_CONT)) != 0;
-    if (__any_sync(full, xrow || tie != 0) || (((carryA | carryB) >> g) & 1u)) {
-        if (__any_sync(full, xrow) || (((carryA | carryB) >> g) & 1u)) {
+    if (__any_sync(full, xrow || tie != 0) || (carryA | carryB) != 0u) {
+        if (__any_sync(full, (fl & (F_EXTRA | F_MULTI_A | F_MULTI_B)) != 0) || (((carryA | carryB) >> g) & 1u)) {
             const MultiOut r = resolve_multi(fl, lane, S.nf - step * 32, g, (unsigned)__double2hiint(hA),
                                              (unsigned)__double2hiint(hB), carryA, carryB);
             hA = __hiloint2double((int)r.hAhi, 0); hB = __hiloint2double((int)r.hBhi, 0);
             carryA = r.carryA; carryB = r.carryB; nm = r.nm; vm = r.vm;
+            special = nm != vm;
+        } else if (__any_sync(full, xrow)) {            /* CONT rows only: no hits to move, just who starts a fragment */
+            const int n = S.nf - step * 32;
+            vm = n >= 32 ? full : ((1u << n) - 1u);
+            nm = __ballot_sync(full, lane < n && !(fl & F_CONT));
             special = nm != vm;
         }
         if (tie != 0 && (fl & (F_PAIRED | F_EXTRA)) == F_PAIRED) {      /* the literal row */
@@ -305,11 +312,24 @@ __device__ __forceinline__ FragOut score_frag_chunk_fast(const SvgtParams &p, co
     o.p_ref = __dmul_rn(prod, wref); o.p_alt = __dmul_rn(prod, walt);
     o.ia = 0; o.ib = 0; o.lead = 0; o.need_idx = false;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {                  /* phase B adds a and b one by one: park their LUT indices */
-        o.ia = hA != 0.0 ? (int)mqA : 0; o.ib = hB != 0.0 ? (int)mqB : 0;
+        o.ia = hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0;
+    } else if (special && ((vm & ~nm) & ~(nm << 1)) == 0u) {
+        /* every continuation row sits right below the row that starts its fragment (and none leads the
+         * chunk): fold_continuations() is one step -- the lower row takes (s_up + a) + b and the weights,
+         * the upper row parks zeros.  Folding weights that are zero anyway changes nothing (x + 0.0). */
+        const unsigned NN = vm & ~nm;
+        const bool cont = (NN >> lane) & 1u, has_next = (NN >> 1 >> lane) & 1u;
+        const double us = __shfl_up_sync(full, o.s, 1), ur = __shfl_up_sync(full, o.p_ref, 1);
+        const double ua = __shfl_up_sync(full, o.p_alt, 1);
+        if (cont) {
+            o.s = __dadd_rn(__dadd_rn(us, __dmul_rn(pmA, hA)), vb);
+            o.p_ref = __dadd_rn(ur, o.p_ref); o.p_alt = __dadd_rn(ua, o.p_alt);
+        }
+        if (has_next) { o.s = 0.0; o.p_ref = 0.0; o.p_alt = 0.0; }
     } else if (special) {
         const FoldOut r = fold_continuations(lane, S.nf - step * 32, nm, vm, __dmul_rn(pmA, hA), vb, o.s, o.p_ref, o.p_alt);
         o.s = r.s; o.p_ref = r.p_ref; o.p_alt = r.p_alt; o.lead = r.lead;
-        if (lane < r.lead) { o.ia = hA != 0.0 ? (int)mqA : 0; o.ib = hB != 0.0 ? (int)mqB : 0; }
+        if (lane < r.lead) { o.ia = hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0; }
     }
     return o;
 }
@@ -385,9 +405,19 @@ __device__ __forceinline__ SplitOut score_split_chunk_lean(const SplitF &F, cons
     const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);       /* (.. + ..) / 2.0, exact either way */
     SplitOut o;
     o.vseq = soft ? 0.0 : p_alt; o.vclip = soft ? p_alt : 0.0; o.lead = 0;
-    if (ASSOC == SVGT_ASSOC_SSO && __any_sync(full, rv && !first)) {     /* extra splits of one fragment: rare */
-        const FoldOut r = fold_splits(lane, n, __ballot_sync(full, rv && first), o.vseq, o.vclip);
-        o.vseq = r.p_ref; o.vclip = r.p_alt; o.lead = r.lead;
+    if (ASSOC == SVGT_ASSOC_SSO && __any_sync(full, rv && !first)) {     /* extra splits of one fragment */
+        const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
+        const unsigned nm = __ballot_sync(full, rv && first);
+        const unsigned NN = vm & ~nm;
+        if ((NN & ~(nm << 1)) == 0u) {                  /* second split right below its first: one fold step */
+            const bool cont = (NN >> lane) & 1u, has_next = (NN >> 1 >> lane) & 1u;
+            const double us = __shfl_up_sync(full, o.vseq, 1), uc = __shfl_up_sync(full, o.vclip, 1);
+            if (cont) { o.vseq = __dadd_rn(us, o.vseq); o.vclip = __dadd_rn(uc, o.vclip); }
+            if (has_next) { o.vseq = 0.0; o.vclip = 0.0; }
+        } else {
+            const FoldOut r = fold_splits(lane, n, nm, o.vseq, o.vclip);
+            o.vseq = r.p_ref; o.vclip = r.p_alt; o.lead = r.lead;
+        }
     }
     return o;
 }
