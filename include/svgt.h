@@ -99,11 +99,13 @@ int svgt_score_batch(const svgt_batch_t *batch, void *out_rows, int32_t *status,
 int svgt_launches_per_batch(const svgt_batch_t *batch);
 
 /*
- * Row-delivery variant of the scoring kernel (same results, different memory path):
+ * Kernel variant (same results, different mapping / memory path):
  * 0 = thread-per-site, per-lane 128-bit global loads with register prefetch; 1 = thread-per-site,
  * per-lane cp.async.bulk (TMA 1-D) ring in shared memory; 2 / 3 = warp-cooperative (row per lane,
- * ordered sums interleaved over 8 / 4 sites per warp; 2 is the default), tally + call kernels.  -1 restores the default (or the
- * SVGT_VARIANT environment variable).  Returns the variant now in force.
+ * ordered sums interleaved over 8 / 4 sites per warp), tally + call kernels; 4 = warp-cooperative with
+ * rows through a cp.async.bulk shared-memory ring; 5 = warp-cooperative with the lean row scorer and a
+ * cp.async row ring (the default).  -1 restores the default (or the SVGT_VARIANT environment
+ * variable).  Returns the variant now in force.  Variants 0-4 are kept as parity cross-checks.
  */
 int svgt_set_variant(int variant);
 
