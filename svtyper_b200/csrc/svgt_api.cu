@@ -117,7 +117,7 @@ int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, voi
     p.n_tiles = (int)((b->n_sites + 31) / 32);
     p.hist_in_smem = (b->n_hist <= SVGT_SMEM_HIST_WORDS) ? 1 : 0;
     const int variant = current_variant();
-    e = (cudaError_t)(variant == SVGT_VAR_LEAN ? svgt_launch_lean(p, st) : variant == SVGT_VAR_RING ? svgt_launch_ring(p, st)
+    e = (cudaError_t)(variant >= SVGT_VAR_LEAN ? svgt_launch_lean(p, variant, st) : variant == SVGT_VAR_RING ? svgt_launch_ring(p, st)
                       : variant >= SVGT_VAR_COOP ? svgt_launch_coop(p, variant, st) : svgt_launch_score(p, variant, st));
     if (e != cudaSuccess) return cuda_fail(e, "svgt_score_kernel launch");
     return SVGT_OK;

@@ -22,8 +22,11 @@ enum {
     SVGT_VAR_COOP = 2,     /* warp-cooperative, 8 sites interleaved per warp (svgt_coop.cu) */
     SVGT_VAR_COOP4 = 3,    /* warp-cooperative, 4 sites interleaved per warp                 */
     SVGT_VAR_RING = 4,     /* warp-cooperative, rows through a cp.async.bulk smem ring (svgt_ring.cu) */
-    SVGT_VAR_LEAN = 5,     /* warp-cooperative with the lean row scorer (svgt_lean.cu), the default         */
-    SVGT_VAR_COUNT = 6
+    SVGT_VAR_LEAN = 5,     /* warp-cooperative with the lean row scorer (svgt_lean.cu), the default:
+                              8 sites per work unit, 2 for small batches                                     */
+    SVGT_VAR_LEAN8 = 6,    /* the same, always 8 sites per unit (tests)                                     */
+    SVGT_VAR_LEAN2 = 7,    /* the same, always 2 sites per unit (tests)                                     */
+    SVGT_VAR_COUNT = 8
 };
 #define SVGT_COOP_THREADS 256       /* 8 warps per CTA in the cooperative kernel     */
 
@@ -53,4 +56,4 @@ size_t svgt_score_smem_bytes(const SvgtParams &p, int variant);
 int svgt_launch_coop(const SvgtParams &p, int variant, cudaStream_t stream);
 int svgt_launch_call(const SvgtParams &p, cudaStream_t stream);
 int svgt_launch_ring(const SvgtParams &p, cudaStream_t stream);
-int svgt_launch_lean(const SvgtParams &p, cudaStream_t stream);
+int svgt_launch_lean(const SvgtParams &p, int variant, cudaStream_t stream);

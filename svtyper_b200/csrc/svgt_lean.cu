@@ -32,7 +32,7 @@ namespace {
 constexpr int kD = SVGT_LEAN_DEPTH;
 constexpr int kLeanWarps = SVGT_LEAN_THREADS / 32;
 constexpr int kHistPad = 8;         /* sentinels behind the cached libraries' counts */
-constexpr int kLeanHistWords = 5120;/* shared-memory budget for the cached counts (the CTA uses ~211 KB besides) */
+constexpr int kLeanHistWords = 4864;/* shared-memory budget for the cached counts (the CTA uses ~211 KB besides) */
 
 /* one row stream of a site: where its rows start and how many there are (one uniform LDS.128 per chunk) */
 struct alignas(16) Strm { const int4 *rows; int n; int pad; };
@@ -47,7 +47,6 @@ struct alignas(128) LeanSmem {
     WinF wf[G][kWLibs + 1];
     Win gwin[kWLibs];               /* windows of the non-fast site being scored */
     Parked park[G];                 /* phase A -> phase B */
-    unsigned newmask[G];
     double zero[2];
 };
 
@@ -187,7 +186,12 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 F.tA = b.z; F.wA0 = a.x - m; F.wA1 = a.x + m; F.wB0 = a.y - m; F.wB1 = a.y + m;
                 F.pat = (meta & (SITE_O1_REV | SITE_O2_REV)) | F_PAIRED;   /* site bits 2,3 line up with F_REV_A/B */
                 F.del = svtype == SV_DEL;
-                F.fast = (a.x - m >= 0) && (a.y - m >= 0) && svtype != SV_INV && b.z == b.w;
+                const bool okwin = (a.x - m >= 0) && (a.y - m >= 0);      /* both is_ref_seq windows valid */
+                F.fast = !okwin ? 0 : (svtype != SV_INV && b.z == b.w) ? 1 : 2;
+                F.tB = b.w; F.inv = svtype == SV_INV;
+                /* make_win(): the reciprocal window starts FL after the alt window for a forward breakend
+                 * (alt [L - FL, H] vs reciprocal [L, H + FL]), FL before it for a reverse one; same width */
+                F.sgnA = (meta & SITE_O1_REV) ? 1 : -1; F.sgnB = (meta & SITE_O2_REV) ? 1 : -1;
                 ws.spf[lane] = make_splitf(S, slop);
                 Strm q;
                 q.pad = 0;
@@ -356,23 +360,34 @@ size_t lean_smem_bytes(const SvgtParams &p)
     return off;
 }
 
+/* per (kernel instantiation, device): opt-in shared memory and the resident-CTA count, queried once */
+struct LeanLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
+
 template <int G>
 int launch_lean(const SvgtParams &p, cudaStream_t stream)
 {
-    auto kern = (p.assoc_mode == SVGT_ASSOC_CLASSIC) ? svgt_lean_kernel<G, SVGT_ASSOC_CLASSIC>
-                                                     : svgt_lean_kernel<G, SVGT_ASSOC_SSO>;
+    static LeanLaunchInfo info[2] = {};
+    const int a = p.assoc_mode == SVGT_ASSOC_CLASSIC ? 1 : 0;
+    auto kern = a ? svgt_lean_kernel<G, SVGT_ASSOC_CLASSIC> : svgt_lean_kernel<G, SVGT_ASSOC_SSO>;
     const size_t smem = lean_smem_bytes<G>(p);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e;
+    int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SVGT_LEAN_THREADS, smem)) != cudaSuccess)
-        return (int)e;
-    if (per_sm < 1) per_sm = 1;
+    LeanLaunchInfo &li = info[a];
+    const int di = dev & 15;
+    if (!li.ready[di] || li.smem_set[di] < smem) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return (int)e;
+        if ((e = cudaDeviceGetAttribute(&li.sms[di], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&li.per_sm[di], kern, SVGT_LEAN_THREADS, smem)) !=
+            cudaSuccess)
+            return (int)e;
+        if (li.per_sm[di] < 1) li.per_sm[di] = 1;
+        li.smem_set[di] = smem; li.ready[di] = 1;
+    }
     const long long units = (p.n_sites + G - 1) / G;
     const long long want = (units + kLeanWarps - 1) / kLeanWarps;
-    const long long cap = (long long)sms * per_sm;      /* persistent: one resident wave */
+    const long long cap = (long long)li.sms[di] * li.per_sm[di];      /* persistent: one resident wave */
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     kern<<<grid, SVGT_LEAN_THREADS, smem, stream>>>(p);
@@ -385,4 +400,14 @@ int launch_lean(const SvgtParams &p, cudaStream_t stream)
 #ifndef SVGT_LEAN_G
 #define SVGT_LEAN_G 8
 #endif
-int svgt_launch_lean(const SvgtParams &p, cudaStream_t stream) { return launch_lean<SVGT_LEAN_G>(p, stream); }
+#ifndef SVGT_LEAN_SMALL_SITES
+#define SVGT_LEAN_SMALL_SITES 40000     /* below ~2 units of 8 sites per resident warp (148 SMs x 16 warps) */
+#endif
+/* Small batches are bound by the longest work unit, not by throughput: two sites per unit spread the
+ * heaviest sites (launch order is work-descending) over four times as many warps. */
+int svgt_launch_lean(const SvgtParams &p, int variant, cudaStream_t stream)
+{
+    const bool two = variant == SVGT_VAR_LEAN2 || (variant == SVGT_VAR_LEAN && p.n_sites < SVGT_LEAN_SMALL_SITES);
+    if (two) return launch_lean<2>(p, stream);
+    return launch_lean<SVGT_LEAN_G>(p, stream);
+}

@@ -33,10 +33,13 @@ constexpr unsigned kOneHi = 0x3FF00000u, kHalfHi = 0x3FE00000u;   /* high words 
 constexpr unsigned kTrapLk = 0x80000000u;
 constexpr int kHistLenBits = 14;                                  /* packed hist length < 16384 */
 
-/* fast-site constants, read warp-uniformly as two LDS.128 */
+/* fast-site constants, read warp-uniformly as two LDS.128 (three for the general chain) */
 struct SiteF {
     int tA, wA0, wA1, wB0;
-    int wB1, pat, del, fast;     /* pat: (fl & 0x5C) of an alt-orientation pair; del: DEL site; fast: lean path valid */
+    int wB1, pat, del, fast;     /* pat: (fl & 0x5C) of an alt-orientation pair; del: DEL site;
+                                    fast: 0 generic scorer, 1 fast_row (one contig, not INV), 2 fast_row_gen */
+    int tB, sgnA, sgnB, inv;     /* general chain: second contig; the reciprocal (INV) alt windows are the alt
+                                    windows shifted by sgn * FL; inv: the site is an inversion */
 };
 
 /* per-(site, library slot); slot kWLibs is the trap entry for library indices beyond the cache */
@@ -171,6 +174,122 @@ __device__ __forceinline__ void fast_row(const int4 lo, const int4 hi, const int
           "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w) /* %19..%26 */);
 }
 
+/*
+ * The same row for a site whose breakends lie on two contigs (BND) and / or an inversion: every test
+ * names its own contig, and an INV pair may also straddle in the reciprocal orientation
+ * (singlesample.py:296-303), whose windows are the alt windows shifted by -/+ FL.
+ */
+__device__ __forceinline__ void fast_row_gen(const int4 lo, const int4 hi, const int4 f0, const int4 f1, const int4 f2,
+                                             const uint4 w0, const uint4 w1, double &hA, double &hB, double &wref,
+                                             double &walt, int &tie)
+{
+    asm("{\n\t"
+        ".reg .pred eaa, eab, eba, ebb, pfl, pf1, pf2, p, q, hA, hB, pe0, pa, prc, pr0, ra, rb, pc, pt, pdel, pinv, both, any, x1, ron, aon, ptrap;\n\t"
+        ".reg .b32 t, u, d, x, o, k2, len, hb, i1, i2, a1, a2, h1, h2, l19, zr;\n\t"
+        "mov.b32 zr, 0;\n\t"
+        "setp.eq.s32 eaa, %9, %12;\n\t"
+        "setp.eq.s32 eab, %9, %27;\n\t"
+        "setp.eq.s32 eba, %10, %12;\n\t"
+        "setp.eq.s32 ebb, %10, %27;\n\t"
+        /* is_ref_seq, read A: on contig tA against window A, on contig tB against window B */
+        "and.b32 t, %11, 1;\n\t"
+        "setp.ne.s32 pfl, t, 0;\n\t"
+        "and.pred pf1, pfl, eaa;\n\t"
+        "and.pred pf2, pfl, eab;\n\t"
+        "setp.le.and.s32 p, %5, %13, pf1;\n\t"
+        "setp.ge.and.s32 p, %6, %14, p;\n\t"
+        "setp.le.and.s32 q, %5, %15, pf2;\n\t"
+        "setp.ge.and.s32 q, %6, %16, q;\n\t"
+        "or.pred hA, p, q;\n\t"
+        "and.b32 t, %11, 2;\n\t"
+        "setp.ne.s32 pfl, t, 0;\n\t"
+        "and.pred pf1, pfl, eba;\n\t"
+        "and.pred pf2, pfl, ebb;\n\t"
+        "setp.le.and.s32 p, %7, %13, pf1;\n\t"
+        "setp.ge.and.s32 p, %8, %14, p;\n\t"
+        "setp.le.and.s32 q, %7, %15, pf2;\n\t"
+        "setp.ge.and.s32 q, %8, %16, q;\n\t"
+        "or.pred hB, p, q;\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hA;\n\t"
+        "mov.b64 %0, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hB;\n\t"
+        "mov.b64 %1, {zr, t};\n\t"
+        /* alt straddle: read A on tA, read B on tB, alt orientation; INV also the reciprocal one */
+        "and.pred pe0, eaa, ebb;\n\t"
+        "and.b32 t, %11, 0x5C;\n\t"
+        "setp.eq.and.s32 pa, t, %17, pe0;\n\t"
+        "sub.s32 d, %5, %19;\n\t"
+        "setp.lt.and.u32 pa, d, %20, pa;\n\t"
+        "sub.s32 d, %8, %21;\n\t"
+        "setp.lt.and.u32 pa, d, %22, pa;\n\t"
+        "setp.ne.s32 pinv, %30, 0;\n\t"
+        "and.pred prc, pe0, pinv;\n\t"
+        "xor.b32 u, %17, 0xC;\n\t"
+        "setp.eq.and.s32 prc, t, u, prc;\n\t"
+        "sub.s32 d, %5, %19;\n\t"
+        "mad.lo.s32 d, %28, %23, d;\n\t"
+        "setp.lt.and.u32 prc, d, %20, prc;\n\t"
+        "sub.s32 d, %8, %21;\n\t"
+        "mad.lo.s32 d, %29, %23, d;\n\t"
+        "setp.lt.and.u32 prc, d, %22, prc;\n\t"
+        "or.pred pa, pa, prc;\n\t"
+        /* reference FR pairs: both reads on tA around A, both on tB around B */
+        "setp.eq.s32 pr0, t, 0x18;\n\t"
+        "and.pred ra, eaa, eba;\n\t"
+        "and.pred ra, ra, pr0;\n\t"
+        "and.pred rb, eab, ebb;\n\t"
+        "and.pred rb, rb, pr0;\n\t"
+        "add.s32 x, %5, %23;\n\t"
+        "sub.s32 d, x, %13;\n\t"
+        "setp.lt.and.u32 ra, d, %24, ra;\n\t"
+        "sub.s32 d, %8, %14;\n\t"
+        "add.s32 d, d, -1;\n\t"
+        "setp.lt.and.u32 ra, d, %24, ra;\n\t"
+        "sub.s32 d, x, %15;\n\t"
+        "setp.lt.and.u32 rb, d, %24, rb;\n\t"
+        "sub.s32 d, %8, %16;\n\t"
+        "add.s32 d, d, -1;\n\t"
+        "setp.lt.and.u32 rb, d, %24, rb;\n\t"
+        /* p_concordant on the counts; keys outside the histogram clamp onto the zero sentinel */
+        "sad.s32 o, %8, %5, 0;\n\t"
+        "sub.s32 k2, o, %25;\n\t"
+        "shr.u32 len, %26, 18;\n\t"
+        "and.b32 hb, %26, 0x3ffff;\n\t"
+        "min.u32 i1, o, len;\n\t"
+        "min.u32 i2, k2, len;\n\t"
+        "mad.lo.u32 a1, i1, 4, hb;\n\t"
+        "mad.lo.u32 a2, i2, 4, hb;\n\t"
+        "ld.shared.u32 h1, [a1];\n\t"
+        "ld.shared.u32 h2, [a2];\n\t"
+        "mul.lo.u32 l19, h1, 19;\n\t"
+        "setp.gt.u32 pc, l19, h2;\n\t"
+        "setp.eq.u32 pt, l19, h2;\n\t"
+        "setp.ne.and.u32 pt, h2, 0, pt;\n\t"
+        "setp.lt.s32 ptrap, %25, 0;\n\t"
+        "or.pred pt, pt, ptrap;\n\t"
+        "selp.s32 %4, 1, 0, pt;\n\t"
+        /* weights */
+        "setp.ne.s32 pdel, %18, 0;\n\t"
+        "and.pred both, ra, rb;\n\t"
+        "or.pred any, ra, rb;\n\t"
+        "and.pred x1, both, !pdel;\n\t"
+        "and.pred ron, any, !x1;\n\t"
+        "and.pred ron, ron, pc;\n\t"
+        "and.pred x1, pdel, pc;\n\t"
+        "and.pred aon, pa, !x1;\n\t"
+        "selp.b32 t, 0x3FF00000, 0x3FE00000, both;\n\t"
+        "selp.b32 t, t, 0, ron;\n\t"
+        "mov.b64 %2, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, aon;\n\t"
+        "mov.b64 %3, {zr, t};\n\t"
+        "}"
+        : "=d"(hA), "=d"(hB), "=d"(wref), "=d"(walt), "=r"(tie)
+        : "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.w),          /* %5..%11  */
+          "r"(f0.x), "r"(f0.y), "r"(f0.z), "r"(f0.w), "r"(f1.x), "r"(f1.y), "r"(f1.z),          /* %12..%18 */
+          "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w), /* %19..%26 */
+          "r"(f2.x), "r"(f2.y), "r"(f2.z), "r"(f2.w)                                             /* %27..%30 */);
+}
+
 /* EXTRA interval rows feed the next main row's MULTI slots; hits of an EXTRA run that reaches the end of
  * the chunk are carried into the site's next chunk (bit g of carryA / carryB).  Same ballots as in
  * score_frag_chunk(); out of line because < 1 % of rows are such rows. */
@@ -272,7 +391,8 @@ __device__ __forceinline__ FragOut score_frag_chunk_fast(const SvgtParams &p, co
 
     double hA, hB, wref, walt;                      /* {0,1}, {0,1}, {0,.5,1}, {0,1} */
     int tie;
-    fast_row(lo, hi, f0, f1, w0, w1, hA, hB, wref, walt, tie);
+    if (f1.w == 1) fast_row(lo, hi, f0, f1, w0, w1, hA, hB, wref, walt, tie);
+    else fast_row_gen(lo, hi, f0, f1, *reinterpret_cast<const int4 *>(&F.tB), w0, w1, hA, hB, wref, walt, tie);
 
     /* one vote for everything rare: EXTRA / MULTI / CONT rows (evidence.py), a p_concordant tie or a
      * library the integer rewrites do not cover; carried EXTRA hits re-enter through the carry bits */

@@ -66,7 +66,8 @@ def test_set_variant(lib):
     assert lib.svgt_set_variant(3) == 3
     assert lib.svgt_set_variant(4) == 4
     assert lib.svgt_set_variant(5) == 5
-    assert lib.svgt_set_variant(-1) in (0, 1, 2, 3, 4, 5)
+    assert lib.svgt_set_variant(7) == 7
+    assert lib.svgt_set_variant(-1) in (0, 1, 2, 3, 4, 5, 6, 7)
 
 
 def test_no_cpu_fallback(lib):

@@ -28,7 +28,7 @@ def gpu_rows(eng, batch, variant=5, **kw):
     return eng.rows(dev)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("assoc", [ev.ASSOC_SSO, ev.ASSOC_CLASSIC])
 def test_reference_fixture(eng, oracle, fixture_batch, fixture_npz, variant, assoc):
     """211 breakpoints of the reference's own test data: golden values from the reference."""
@@ -40,7 +40,7 @@ def test_reference_fixture(eng, oracle, fixture_batch, fixture_npz, variant, ass
     assert_rows_match(got, oracle.score(fixture_batch, assoc_mode=assoc), exact_gl=True, where="fixture")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("config,n", [("del10k", 10_000), ("mixed100k", 20_000), ("del1m4lib", 20_000),
                                       ("stress1m", 6_000)])
 def test_synthetic_configs(eng, oracle, config, n, variant):
@@ -53,7 +53,7 @@ def test_synthetic_configs(eng, oracle, config, n, variant):
         assert (exp["GT"] == ev.GT_UNDERFLOW).any()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_hazard_vectors(eng, oracle, variant):
     b = synth.hazard_batch()
     got = gpu_rows(eng, b, variant)
@@ -61,7 +61,7 @@ def test_hazard_vectors(eng, oracle, variant):
     assert got["RS"][0] == 26 and got["RP"][0] == 12        # sequential, not tree, sums
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_classic_association_and_weights(eng, oracle, variant):
     b = synth.generate("mixed100k", n_sites=3000, seed=77)
     for assoc in (ev.ASSOC_SSO, ev.ASSOC_CLASSIC):
@@ -84,7 +84,7 @@ def test_empty_batch(eng):
     assert eng.score_host(b).shape == (0,)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_literal_path_for_unsafe_library(eng, oracle, variant):
     """flank = mean + 3 sd within 1e-9 of an integer: the integer window rewrite is not
     provably exact, so the kernel must take the literal fp64 comparisons."""
@@ -118,7 +118,7 @@ def test_many_libraries_and_large_histogram(eng, oracle):
     big = ev.LibraryTable([synth.gaussian_library(4000, 900)])
     assert big.hist.size > 6144
     b = synth.generate("del10k", n_sites=2000, seed=10, libs=big)
-    for v in (0, 1, 2, 3, 4, 5):
+    for v in (0, 1, 2, 3, 4, 5, 6, 7):
         assert_rows_match(gpu_rows(eng, b, v), oracle.score(b), exact_gl=True, where="big hist")
 
 
