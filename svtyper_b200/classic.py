@@ -12,7 +12,7 @@ import os
 import sys
 
 from . import evidence as ev
-from . import gather, genotype, vcf
+from . import gather, genotype, packer, vcf
 from .sample import SampleInfo, write_sample_json
 
 
@@ -86,7 +86,8 @@ def sv_genotype(bam_string,
     rows = {}
     for s in samples:
         batch = genotype.pack_sample(
-            s, plan, lambda smp, bp: gather.gather_classic(smp, bp, genotype.Z, max_reads), min_aligned)
+            s, plan, lambda smp, bp: gather.gather_classic(smp, bp, genotype.Z, max_reads), min_aligned,
+            mode=packer.MODE_CLASSIC, max_reads=max_reads)
         rows[s.name] = genotype.score(batch, min_aligned=min_aligned, split_slop=genotype.SPLIT_SLOP,
                                       split_weight=split_weight, disc_weight=disc_weight,
                                       assoc_mode=ev.ASSOC_CLASSIC)

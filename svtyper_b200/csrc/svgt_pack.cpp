@@ -1,0 +1,849 @@
+/*
+ * svgt_pack.cpp -- native evidence packer (libsvgt_pack.so): BGZF + BAI region reader, read gathering,
+ * split-candidate QC and row packing for a batch of breakpoints.  C ABI and reference citations:
+ * include/svgt_pack.h.  Behaviour is pinned to svtyper_b200/gather.py + evidence.BatchPacker (themselves
+ * pinned to the reference through the golden VCF) by tests/test_pack_native.py.
+ *
+ * Host code only (no CUDA): read gathering stays on the CPU by design.
+ */
+#include "../../include/svgt_pack.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <map>
+#include <memory>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+/* ---- schema constants (svtyper_b200/evidence.py) ---- */
+enum {
+    F_HAS_A = 1 << 0, F_HAS_B = 1 << 1, F_REV_A = 1 << 2, F_REV_B = 1 << 3, F_PAIRED = 1 << 4,
+    F_CONT = 1 << 5, F_EXTRA = 1 << 6, F_MULTI_A = 1 << 7, F_MULTI_B = 1 << 8
+};
+enum { S_SOFT_CLIP = 1 << 0, S_FIRST = 1 << 1 };
+const int TID_NONE = -2;
+enum { FUNMAP = 0x4, FREVERSE = 0x10, FSECONDARY = 0x100, FQCFAIL = 0x200, FDUP = 0x400, FSUPPLEMENTARY = 0x800 };
+/* reference parsers.py:960-962 */
+const int MIN_NON_OVERLAP = 20, MIN_INDEL = 50, MAX_UNMAPPED_BASES = 50;
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+/* CIGAR op classes, MIDNSHP=X */
+inline bool consumes_ref(int op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+inline bool is_aligned(int op) { return op == 0 || op == 7 || op == 8; }
+inline bool consumes_query_aln(int op) { return op == 0 || op == 1 || op == 7 || op == 8; }
+inline bool is_clip(int op) { return op == 4 || op == 5; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* BGZF: random access by virtual offset, a small cache of inflated blocks                      */
+/* ------------------------------------------------------------------------------------------ */
+struct Block { std::vector<uint8_t> data; uint32_t csize = 0; uint64_t stamp = 0; };
+
+class Bgzf {
+public:
+    ~Bgzf() { if (f_) fclose(f_); }
+    bool open(const char *path) { f_ = fopen(path, "rb"); return f_ != nullptr; }
+    bool seek(uint64_t voff) { if (!load(voff >> 16)) return false; uoff_ = (uint32_t)(voff & 0xFFFF); return true; }
+    uint64_t tell() const
+    {
+        if (cur_ && uoff_ >= cur_->data.size() && cur_->csize) return (coff_ + cur_->csize) << 16;
+        return (coff_ << 16) | uoff_;
+    }
+    /* read up to n bytes; returns the number read, or -1 on a corrupt file */
+    long read(uint8_t *dst, size_t n)
+    {
+        size_t got = 0;
+        while (n > 0) {
+            if (!cur_) return -1;
+            const size_t avail = cur_->data.size() > uoff_ ? cur_->data.size() - uoff_ : 0;
+            if (avail == 0) {
+                if (cur_->csize == 0) break;                  /* end of file */
+                if (!load(coff_ + cur_->csize)) return -1;
+                uoff_ = 0;
+                if (cur_->csize == 0) break;
+                continue;
+            }
+            const size_t take = avail < n ? avail : n;
+            memcpy(dst + got, cur_->data.data() + uoff_, take);
+            uoff_ += (uint32_t)take; got += take; n -= take;
+        }
+        return (long)got;
+    }
+
+private:
+    bool load(uint64_t coff)
+    {
+        auto it = cache_.find(coff);
+        if (it != cache_.end()) { cur_ = &it->second; cur_->stamp = ++clock_; coff_ = coff; return true; }
+        if (cache_.size() >= 512) {                           /* drop the older half */
+            std::vector<std::pair<uint64_t, uint64_t>> age;
+            for (auto &kv : cache_) age.push_back({kv.second.stamp, kv.first});
+            std::sort(age.begin(), age.end());
+            for (size_t i = 0; i < age.size() / 2; ++i) cache_.erase(age[i].second);
+        }
+        Block b;
+        uint8_t hdr[18];
+        if (fseeko(f_, (off_t)coff, SEEK_SET) != 0) return false;
+        const size_t nh = fread(hdr, 1, 18, f_);
+        if (nh == 18) {
+            if (!(hdr[0] == 0x1f && hdr[1] == 0x8b && hdr[2] == 8 && hdr[3] == 4)) return false;
+            const unsigned xlen = rd16(hdr + 10);
+            std::vector<uint8_t> extra(xlen);
+            memcpy(extra.data(), hdr + 12, xlen < 6 ? xlen : 6);
+            if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != xlen - 6) return false;
+            int bsize = -1;
+            for (size_t p = 0; p + 4 <= extra.size();) {
+                const unsigned slen = rd16(extra.data() + p + 2);
+                if (extra[p] == 66 && extra[p + 1] == 67 && p + 6 <= extra.size()) bsize = rd16(extra.data() + p + 4);
+                p += 4 + slen;
+            }
+            if (bsize < 0) return false;
+            b.csize = (uint32_t)bsize + 1;
+            const long plen = (long)b.csize - 12 - (long)xlen - 8;
+            if (plen < 0) return false;
+            std::vector<uint8_t> payload((size_t)plen);
+            uint8_t tail[8];
+            if (plen && fread(payload.data(), 1, (size_t)plen, f_) != (size_t)plen) return false;
+            if (fread(tail, 1, 8, f_) != 8) return false;
+            const uint32_t isize = rd32(tail + 4);
+            b.data.resize(isize);
+            if (isize) {
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (inflateInit2(&zs, -15) != Z_OK) return false;
+                zs.next_in = payload.data(); zs.avail_in = (uInt)plen;
+                zs.next_out = b.data.data(); zs.avail_out = isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (rc != Z_STREAM_END || zs.total_out != isize) return false;
+            }
+        }                                                     /* short read: end of file, empty block */
+        b.stamp = ++clock_;
+        auto ins = cache_.emplace(coff, std::move(b));
+        cur_ = &ins.first->second; coff_ = coff;
+        return true;
+    }
+
+    FILE *f_ = nullptr;
+    std::unordered_map<uint64_t, Block> cache_;
+    Block *cur_ = nullptr;
+    uint64_t coff_ = 0, clock_ = 0;
+    uint32_t uoff_ = 0;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* BAI                                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+struct RefIndex {
+    std::unordered_map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+    std::vector<uint64_t> linear;
+};
+
+struct Bai {
+    std::vector<RefIndex> refs;
+
+    bool load(const char *path)
+    {
+        FILE *f = fopen(path, "rb");
+        if (!f) return false;
+        std::vector<uint8_t> b;
+        uint8_t tmp[65536];
+        size_t n;
+        while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) b.insert(b.end(), tmp, tmp + n);
+        fclose(f);
+        if (b.size() < 8 || memcmp(b.data(), "BAI\1", 4) != 0) return false;
+        size_t p = 4;
+        const int n_ref = (int)rd32(&b[p]); p += 4;
+        refs.resize(n_ref < 0 ? 0 : n_ref);
+        for (auto &r : refs) {
+            if (p + 4 > b.size()) return false;
+            const int n_bin = (int)rd32(&b[p]); p += 4;
+            for (int i = 0; i < n_bin; ++i) {
+                if (p + 8 > b.size()) return false;
+                const uint32_t bin = rd32(&b[p]);
+                const int n_chunk = (int)rd32(&b[p + 4]); p += 8;
+                if (n_chunk < 0 || p + 16 * (size_t)n_chunk > b.size()) return false;
+                if (bin != 37450) {                               /* 37450: htslib's per-reference counts */
+                    auto &v = r.bins[bin];
+                    for (int k = 0; k < n_chunk; ++k) v.push_back({rd64(&b[p + 16 * k]), rd64(&b[p + 16 * k + 8])});
+                }
+                p += 16 * (size_t)n_chunk;
+            }
+            if (p + 4 > b.size()) return false;
+            const int n_intv = (int)rd32(&b[p]); p += 4;
+            if (n_intv < 0 || p + 8 * (size_t)n_intv > b.size()) return false;
+            r.linear.resize(n_intv);
+            for (int k = 0; k < n_intv; ++k) r.linear[k] = rd64(&b[p + 8 * k]);
+            p += 8 * (size_t)n_intv;
+        }
+        return true;
+    }
+
+    /* merged, sorted chunks that may hold records overlapping [beg, end) */
+    std::vector<std::pair<uint64_t, uint64_t>> chunks(int tid, int64_t beg, int64_t end) const
+    {
+        std::vector<std::pair<uint64_t, uint64_t>> out;
+        if (tid < 0 || tid >= (int)refs.size()) return out;
+        const RefIndex &r = refs[tid];
+        const size_t w = (size_t)(beg >> 14);
+        const uint64_t min_off = w < r.linear.size() ? r.linear[w] : (r.linear.empty() ? 0 : r.linear.back());
+        auto add_bin = [&](uint32_t bin) {
+            auto it = r.bins.find(bin);
+            if (it == r.bins.end()) return;
+            for (auto &c : it->second) if (c.second > min_off) out.push_back(c);
+        };
+        const int64_t e = end - 1;
+        add_bin(0);
+        const int shift[5] = {26, 23, 20, 17, 14};
+        const uint32_t base[5] = {1, 9, 73, 585, 4681};
+        for (int l = 0; l < 5; ++l)
+            for (int64_t k = base[l] + (beg >> shift[l]); k <= base[l] + (e >> shift[l]); ++k) add_bin((uint32_t)k);
+        std::sort(out.begin(), out.end());
+        std::vector<std::pair<uint64_t, uint64_t>> merged;
+        for (auto &c : out) {
+            if (!merged.empty() && c.first <= merged.back().second) {
+                if (c.second > merged.back().second) merged.back().second = c.second;
+            } else merged.push_back(c);
+        }
+        return merged;
+    }
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* one BAM record (what the gatherer keeps of it)                                               */
+/* ------------------------------------------------------------------------------------------ */
+struct Read {
+    int32_t tid = -1, pos = 0, end = 0, mapq = 0, flag = 0, l_seq = 0;
+    std::string qname;
+    std::vector<std::pair<int, int>> cigar;       /* (op, len) */
+    std::string rg, sa;
+    bool has_rg = false, has_sa = false;
+    bool is_reverse() const { return (flag & FREVERSE) != 0; }
+};
+
+/* scan the aux block for the RG and SA strings; false on a malformed block */
+bool parse_tags(const uint8_t *b, size_t n, Read &r)
+{
+    size_t p = 0;
+    while (p + 3 <= n) {
+        const char k0 = (char)b[p], k1 = (char)b[p + 1], t = (char)b[p + 2];
+        p += 3;
+        size_t sz = 0;
+        switch (t) {
+        case 'A': case 'c': case 'C': sz = 1; break;
+        case 's': case 'S': sz = 2; break;
+        case 'i': case 'I': case 'f': sz = 4; break;
+        case 'Z': case 'H': {
+            const void *e = memchr(b + p, 0, n - p);
+            if (!e) return false;
+            const size_t len = (const uint8_t *)e - (b + p);
+            if (t == 'Z' && k0 == 'R' && k1 == 'G') { r.rg.assign((const char *)b + p, len); r.has_rg = true; }
+            if (t == 'Z' && k0 == 'S' && k1 == 'A') { r.sa.assign((const char *)b + p, len); r.has_sa = true; }
+            p += len + 1;
+            continue;
+        }
+        case 'B': {
+            if (p + 5 > n) return false;
+            const char sub = (char)b[p];
+            const uint32_t cnt = rd32(b + p + 1);
+            const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+            sz = 5 + es * (size_t)cnt;
+            break;
+        }
+        default: return false;
+        }
+        if (p + sz > n) return false;
+        p += sz;
+    }
+    return true;
+}
+
+/* what every reader of one BAM shares (read-only after open) */
+struct Shared {
+    std::string path;
+    Bai bai;
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    std::unordered_map<std::string, int> tid_of;
+    uint64_t first_record = 0;
+};
+
+/* one reader: its own file handle, block cache and record buffer (one per worker thread) */
+struct svgt_bam_impl {
+    Bgzf bgzf;
+    std::shared_ptr<Shared> sh;
+    std::vector<uint8_t> buf;
+    std::vector<int32_t> frags, splits;               /* rows of the last svgt_pack_sites() */
+};
+
+/* next record at the reader's position: 1 = ok, 0 = end of file, -1 = corrupt */
+int next_record(svgt_bam_impl &B, Read &r, bool want_tags)
+{
+    uint8_t szb[4];
+    const long g = B.bgzf.read(szb, 4);
+    if (g < 0) return -1;
+    if (g < 4) return 0;
+    const uint32_t sz = rd32(szb);
+    if (sz < 32 || sz > (1u << 28)) return -1;
+    B.buf.resize(sz);
+    if (B.bgzf.read(B.buf.data(), sz) != (long)sz) return -1;
+    const uint8_t *b = B.buf.data();
+    r.tid = (int32_t)rd32(b); r.pos = (int32_t)rd32(b + 4);
+    const unsigned l_name = b[8];
+    r.mapq = b[9];
+    const unsigned n_cig = rd16(b + 12);
+    r.flag = rd16(b + 14);
+    r.l_seq = (int32_t)rd32(b + 16);
+    size_t p = 32;
+    if (p + l_name + 4 * (size_t)n_cig > sz || l_name == 0) return -1;
+    r.qname.assign((const char *)b + p, l_name - 1);
+    p += l_name;
+    r.cigar.resize(n_cig);
+    int64_t e = r.pos;
+    for (unsigned i = 0; i < n_cig; ++i) {
+        const uint32_t v = rd32(b + p + 4 * i);
+        r.cigar[i] = {(int)(v & 0xF), (int)(v >> 4)};
+        if (consumes_ref((int)(v & 0xF))) e += (int)(v >> 4);
+    }
+    r.end = (int32_t)e;
+    p += 4 * (size_t)n_cig;
+    p += ((size_t)r.l_seq + 1) / 2 + (size_t)r.l_seq;
+    r.has_rg = r.has_sa = false;
+    if (want_tags) {
+        if (p > sz) return -1;
+        if (!parse_tags(b + p, sz - p, r)) return -1;
+    }
+    return 1;
+}
+
+/* pysam fetch(): file-order records of contig `tid` with pos < end and reference_end > beg.
+ * `fn(read)` returns false to stop.  Returns 0 or a negative error. */
+template <class Fn>
+int fetch(svgt_bam_impl &B, int tid, int64_t beg, int64_t end, bool want_tags, Fn fn)
+{
+    if (tid < 0 || tid >= (int)B.sh->ref_names.size()) return fail(SVGT_PACK_ERR_ARG, "invalid contig id %d", tid);
+    if (beg < 0) beg = 0;
+    if (end <= beg) return 0;
+    Read r;
+    for (auto &c : B.sh->bai.chunks(tid, beg, end)) {
+        if (!B.bgzf.seek(c.first)) return fail(SVGT_PACK_ERR_IO, "BGZF seek failed");
+        while (B.bgzf.tell() < c.second) {
+            const int rc = next_record(B, r, want_tags);
+            if (rc < 0) return fail(SVGT_PACK_ERR_IO, "corrupt BAM record");
+            if (rc == 0) break;
+            if (r.tid != tid || r.pos >= end) return 0;       /* ends the whole query */
+            int64_t rend = r.end;
+            if ((r.flag & FUNMAP) || r.cigar.empty() || rend <= r.pos) rend = (int64_t)r.pos + 1;
+            if (rend > beg) { if (!fn(r)) return 0; }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* split candidates (gather.py: Piece, split_candidate)                                         */
+/* ------------------------------------------------------------------------------------------ */
+struct Piece {
+    int tid = TID_NONE;            /* TID_NONE: chrom None / not in the header */
+    std::string chrom;             /* name as the reference compares it        */
+    bool has_chrom = false;
+    int start = 0, end = 0, mapq = 0;
+    bool rev = false;
+    int qstart = 0, qend = 0, qlen = 0;
+
+    void span(const std::vector<std::pair<int, int>> &cigar)
+    {
+        int s = 0, e = 0, l = 0;
+        const int n = (int)cigar.size();
+        for (int i = 0; i < n; ++i) {
+            const auto &c = rev ? cigar[n - 1 - i] : cigar[i];
+            if (is_clip(c.first)) { if (i == 0) { s += c.second; e += c.second; } l += c.second; }
+            else if (consumes_query_aln(c.first)) { e += c.second; l += c.second; }
+        }
+        qstart = s; qend = e; qlen = l;
+    }
+    int start_diagonal() const { return start - (rev ? (qlen - qend) : qstart); }
+    int end_diagonal() const { return end - (rev ? (qlen - qstart) : qend); }
+};
+
+struct Split { Piece left, right; bool soft = false; };
+
+bool left_clipped(const std::vector<std::pair<int, int>> &cigar)
+{
+    const bool l = is_clip(cigar.front().first), r = is_clip(cigar.back().first);
+    return (l && !r) || (l && r && cigar.front().second > cigar.back().second);
+}
+
+/* '36M2D64M' -> ops, as the regex (\d+)([MIDNSHP=X]) finds them */
+std::vector<std::pair<int, int>> cigar_from_string(const std::string &t)
+{
+    static const char ops[] = "MIDNSHP=X";
+    std::vector<std::pair<int, int>> out;
+    size_t i = 0;
+    while (i < t.size()) {
+        if (t[i] < '0' || t[i] > '9') { ++i; continue; }
+        long v = 0;
+        size_t j = i;
+        while (j < t.size() && t[j] >= '0' && t[j] <= '9') { v = v * 10 + (t[j] - '0'); ++j; }
+        if (j < t.size()) {
+            const char *q = strchr(ops, t[j]);
+            if (q && t[j]) { out.push_back({(int)(q - ops), (int)v}); i = j + 1; continue; }
+        }
+        /* digits not followed by an op: the regex restarts one character further */
+        i = i + 1;
+    }
+    return out;
+}
+
+/* 1 = candidate in `out`, 0 = none, negative = error */
+int split_candidate(const svgt_bam_impl &B, const Read &r, Split &out)
+{
+    if (r.cigar.empty()) return fail(SVGT_PACK_ERR_RECORD, "mapped read %s has no CIGAR", r.qname.c_str());
+    Piece own;
+    own.tid = r.tid; own.has_chrom = r.tid >= 0 && r.tid < (int)B.sh->ref_names.size();
+    if (own.has_chrom) own.chrom = B.sh->ref_names[r.tid];
+    own.start = r.pos; own.end = r.end; own.rev = r.is_reverse(); own.mapq = r.mapq;
+    own.span(r.cigar);
+    if (!r.has_sa) {
+        const bool first = is_clip(r.cigar.front().first), last = is_clip(r.cigar.back().first);
+        if (!(first || last)) return 0;
+        const int longest = std::max(first ? r.cigar.front().second : 0, last ? r.cigar.back().second : 0);
+        int qal = 0;
+        for (auto &c : r.cigar) if (consumes_query_aln(c.first)) qal += c.second;
+        if (longest > 0 && (r.l_seq - qal) <= MAX_UNMAPPED_BASES) {
+            Piece ghost;
+            ghost.tid = TID_NONE; ghost.start = 1; ghost.end = 1; ghost.rev = own.rev; ghost.mapq = 0;
+            ghost.span(r.cigar);
+            out.soft = true;
+            if (left_clipped(r.cigar)) { out.left = ghost; out.right = own; }
+            else { out.left = own; out.right = ghost; }
+            return 1;
+        }
+        return 0;
+    }
+    /* entries = SA.rstrip(';').split(';'); more than one supplementary alignment: not a candidate */
+    std::string sa = r.sa;
+    while (!sa.empty() && sa.back() == ';') sa.pop_back();
+    if (sa.find(';') != std::string::npos) return 0;
+    std::vector<std::string> f;
+    size_t s0 = 0;
+    while (f.size() < 5) {
+        const size_t c = sa.find(',', s0);
+        if (c == std::string::npos) { f.push_back(sa.substr(s0)); break; }
+        f.push_back(sa.substr(s0, c - s0));
+        s0 = c + 1;
+    }
+    if (f.size() < 5) return fail(SVGT_PACK_ERR_RECORD, "malformed SA tag on read %s", r.qname.c_str());
+    char *endp = nullptr;
+    const long sa_pos = strtol(f[1].c_str(), &endp, 10);
+    if (endp == f[1].c_str()) return fail(SVGT_PACK_ERR_RECORD, "malformed SA position on read %s", r.qname.c_str());
+    const long sa_mapq = strtol(f[4].c_str(), &endp, 10);
+    if (endp == f[4].c_str()) return fail(SVGT_PACK_ERR_RECORD, "malformed SA mapq on read %s", r.qname.c_str());
+    const auto mcig = cigar_from_string(f[3]);
+    Piece mate;
+    mate.chrom = f[0]; mate.has_chrom = true;
+    auto it = B.sh->tid_of.find(f[0]);
+    mate.tid = it == B.sh->tid_of.end() ? TID_NONE : it->second;
+    mate.start = (int)sa_pos - 1;                     /* SA is one-based */
+    int e = mate.start;
+    for (auto &c : mcig) if (consumes_ref(c.first)) e += c.second;
+    mate.end = e; mate.rev = f[2] == "-"; mate.mapq = (int)sa_mapq;
+    mate.span(mcig);
+    bool mate_left;
+    if (own.has_chrom && own.chrom == mate.chrom) mate_left = own.start > mate.start;
+    else mate_left = left_clipped(r.cigar);
+    const Piece &L = mate_left ? mate : own, &R = mate_left ? own : mate;
+    /* the two pieces must each cover enough of the read that the other does not */
+    const int overlap = std::max(0, 1 + std::min(L.qend, R.qend) - std::max(L.qstart, R.qstart));
+    if (std::min(1 + L.qend - L.qstart - overlap, 1 + R.qend - R.qstart - overlap) < MIN_NON_OVERLAP) return 0;
+    if (L.has_chrom && R.has_chrom && L.chrom == R.chrom && L.rev == R.rev) {
+        const int ins = L.rev ? R.end_diagonal() - L.start_diagonal() : L.end_diagonal() - R.start_diagonal();
+        if (std::abs(ins) < MIN_INDEL) return 0;
+        const int desert = R.qstart - L.qend - 1;
+        if (desert > 0 && desert - std::max(0, ins) > MAX_UNMAPPED_BASES) return 0;
+    }
+    out.soft = false; out.left = L; out.right = R;
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* fragments and rows (gather.py: Fragment, _collect; evidence.py: BatchPacker._pack_fragment)   */
+/* ------------------------------------------------------------------------------------------ */
+struct Prim {
+    int32_t tid, pos, end, mapq;
+    bool rev;
+    std::vector<std::pair<int, int>> iv;          /* merged gap-free aligned intervals */
+};
+
+struct Fragment {
+    int lib = 0;
+    std::vector<Prim> prim;
+    std::vector<Split> splits;
+    std::unordered_set<int> seen_flags;           /* (query_name, flag) seen; the name is the map key */
+};
+
+Prim make_prim(const Read &r)
+{
+    Prim p;
+    p.tid = r.tid; p.pos = r.pos; p.end = r.end; p.mapq = r.mapq; p.rev = r.is_reverse();
+    int pos = r.pos;
+    for (auto &c : r.cigar) {
+        if (is_aligned(c.first)) {
+            const int s = pos, e = pos + c.second;
+            if (!p.iv.empty() && s == p.iv.back().second) p.iv.back().second = e;
+            else if (e > s) p.iv.push_back({s, e});
+        }
+        if (consumes_ref(c.first)) pos += c.second;
+    }
+    return p;
+}
+
+struct Gather {
+    svgt_bam_impl &B;
+    const std::unordered_map<std::string, int> &rg_lib;
+    const uint8_t *lib_active;
+    int n_lib;
+    std::map<std::string, Fragment> frags;        /* std::map: iteration = sorted(query_name), bytewise */
+    int err = 0;
+
+    /* one fetched record (gather.py _collect body); false = stop with `err` set */
+    bool add(const Read &r)
+    {
+        if (r.flag & (FUNMAP | FDUP)) return true;
+        if (!r.has_rg) { err = fail(SVGT_PACK_ERR_RG, "read %s has no RG tag", r.qname.c_str()); return false; }
+        auto it = rg_lib.find(r.rg);
+        if (it == rg_lib.end() || it->second < 0 || it->second >= n_lib) {
+            err = fail(SVGT_PACK_ERR_RG, "read group %s is not in the library table", r.rg.c_str());
+            return false;
+        }
+        if (!lib_active[it->second]) return true;
+        return keep(r, it->second);
+    }
+    /* the part after the library filter; split out so the classic limit test can sit between them */
+    bool keep(const Read &r, int lib)
+    {
+        auto ins = frags.find(r.qname);
+        if (ins == frags.end()) { ins = frags.emplace(r.qname, Fragment()).first; ins->second.lib = lib; }
+        Fragment &f = ins->second;
+        if (!f.seen_flags.insert(r.flag).second) return true;
+        if (r.flag & (FSUPPLEMENTARY | FSECONDARY)) return true;
+        f.prim.push_back(make_prim(r));
+        Split sp;
+        const int rc = split_candidate(B, r, sp);
+        if (rc < 0) { err = rc; return false; }
+        if (rc > 0) f.splits.push_back(sp);
+        return true;
+    }
+};
+
+void push_row(std::vector<int32_t> &v, const int32_t w[8]) { v.insert(v.end(), w, w + 8); }
+
+void pack_fragment(const Fragment &f, int ordinal, std::vector<int32_t> &frows, std::vector<int32_t> &srows, int &nf,
+                   int &ns)
+{
+    struct Group { const Prim *a, *b; int fl; };
+    std::vector<Group> groups;
+    if (f.prim.size() == 2) groups.push_back({&f.prim[0], &f.prim[1], F_PAIRED});
+    else for (size_t i = 0; i < f.prim.size(); ++i) groups.push_back({&f.prim[i], nullptr, i > 0 ? F_CONT : 0});
+    const int lib = f.lib & 0xFFFF;
+    for (auto &g : groups) {
+        static const std::vector<std::pair<int, int>> none;
+        auto multi = [](const Prim *p) {
+            return p && !(p->iv.size() == 1 && p->iv[0].first == p->pos && p->iv[0].second == p->end);
+        };
+        const bool ma = multi(g.a), mb = multi(g.b);
+        const auto &xa = ma ? g.a->iv : none;
+        const auto &xb = mb ? g.b->iv : none;
+        for (size_t k = 0; k < std::max(xa.size(), xb.size()); ++k) {
+            int32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int efl = F_EXTRA | (g.fl & F_CONT);
+            if (k < xa.size()) { efl |= F_HAS_A; w[0] = xa[k].first; w[1] = xa[k].second; w[4] = g.a->tid; }
+            if (k < xb.size()) { efl |= F_HAS_B; w[2] = xb[k].first; w[3] = xb[k].second; w[5] = g.b->tid; }
+            w[6] = (int32_t)((uint32_t)lib << 16);
+            w[7] = efl;
+            push_row(frows, w); ++nf;
+        }
+        int32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int fl = g.fl;
+        uint32_t w6 = 0;
+        if (g.a) {
+            fl |= F_HAS_A | (g.a->rev ? F_REV_A : 0) | (ma ? F_MULTI_A : 0);
+            w[0] = g.a->pos; w[1] = g.a->end; w[4] = g.a->tid;
+            w6 |= (uint32_t)std::min(g.a->mapq, 255);
+        }
+        if (g.b) {
+            fl |= F_HAS_B | (g.b->rev ? F_REV_B : 0) | (mb ? F_MULTI_B : 0);
+            w[2] = g.b->pos; w[3] = g.b->end; w[5] = g.b->tid;
+            w6 |= (uint32_t)std::min(g.b->mapq, 255) << 8;
+        }
+        w6 |= (uint32_t)lib << 16;
+        w[6] = (int32_t)w6; w[7] = fl;
+        push_row(frows, w); ++nf;
+    }
+    for (size_t i = 0; i < f.splits.size(); ++i) {
+        const Split &s = f.splits[i];
+        const int sfl = (s.soft ? S_SOFT_CLIP : 0) | (i == 0 ? S_FIRST : 0);
+        const uint32_t meta = (uint32_t)std::min(s.left.mapq, 255) | ((uint32_t)std::min(s.right.mapq, 255) << 8) |
+                              ((uint32_t)sfl << 16);
+        const int32_t w[8] = {s.left.tid < 0 ? TID_NONE : s.left.tid, s.left.start, s.left.end,
+                              s.right.tid < 0 ? TID_NONE : s.right.tid, s.right.start, s.right.end, (int32_t)meta,
+                              ordinal};
+        push_row(srows, w); ++ns;
+    }
+}
+
+int64_t count_region(svgt_bam_impl &B, int tid, int64_t beg, int64_t end, bool filter_all)
+{
+    int64_t n = 0;
+    const int rc = fetch(B, tid, beg, end, false, [&](const Read &r) {
+        if (!filter_all || !(r.flag & (FUNMAP | FSECONDARY | FQCFAIL | FDUP))) ++n;
+        return true;
+    });
+    return rc < 0 ? rc : n;
+}
+
+struct PackJob {
+    const std::unordered_map<std::string, int> &rgmap;
+    const uint8_t *lib_active;
+    int n_lib, mode;
+    int64_t max_reads;
+};
+
+/* gather + pack one breakpoint with reader B; rows are appended to frows / srows */
+int pack_one_site(svgt_bam_impl &B, const PackJob &J, const svgt_pack_site_t &S, svgt_pack_count_t &C,
+                  std::vector<int32_t> &frows, std::vector<int32_t> &srows)
+{
+    C.n_frag_rows = C.n_split_rows = C.skip = C.n_fragments = 0;
+    const int tid[2] = {S.tidA, S.tidB};
+    const int64_t beg[2] = {S.begA, S.begB}, end[2] = {S.endA, S.endB};
+    Gather G{B, J.rgmap, J.lib_active, J.n_lib, {}, 0};
+    bool too_many = false;
+    if (J.mode == SVGT_PACK_MODE_SSO) {
+        if (J.max_reads >= 0) {
+            for (int s = 0; s < 2 && !too_many; ++s) {
+                const int64_t n = count_region(B, tid[s], beg[s], end[s], true);
+                if (n < 0) return (int)n;
+                if (n > J.max_reads) too_many = true;
+            }
+        }
+        for (int s = 0; s < 2 && !too_many; ++s) {
+            const int rc = fetch(B, tid[s], beg[s], end[s], true, [&](const Read &r) { return G.add(r); });
+            if (rc < 0) return rc;
+            if (G.err) return G.err;
+        }
+    } else {
+        /* classic.py:79-91: the limit is on the record's index in the fetch, tested after the
+         * duplicate / library filters, so a filtered record never trips it */
+        for (int s = 0; s < 2 && !too_many; ++s) {
+            int64_t i = 0;
+            const int rc = fetch(B, tid[s], beg[s], end[s], true, [&](const Read &r) {
+                const int64_t idx = i++;
+                if (r.flag & (FUNMAP | FDUP)) return true;
+                if (!r.has_rg) { G.err = fail(SVGT_PACK_ERR_RG, "read %s has no RG tag", r.qname.c_str()); return false; }
+                auto it = J.rgmap.find(r.rg);
+                if (it == J.rgmap.end() || it->second < 0 || it->second >= J.n_lib) {
+                    G.err = fail(SVGT_PACK_ERR_RG, "read group %s is not in the library table", r.rg.c_str());
+                    return false;
+                }
+                if (!J.lib_active[it->second]) return true;
+                if (J.max_reads >= 0 && idx > J.max_reads) { too_many = true; return false; }
+                return G.keep(r, it->second);
+            });
+            if (rc < 0) return rc;
+            if (G.err) return G.err;
+        }
+    }
+    if (too_many) { C.skip = 1; return 0; }
+    int ordinal = 0, nf = 0, ns = 0;
+    for (auto &kv : G.frags) pack_fragment(kv.second, ordinal++, frows, srows, nf, ns);
+    C.n_frag_rows = nf; C.n_split_rows = ns; C.n_fragments = ordinal;
+    return 0;
+}
+
+}  // namespace
+
+struct svgt_bam { svgt_bam_impl impl; };
+
+extern "C" {
+
+int svgt_pack_abi_version(void) { return SVGT_PACK_ABI_VERSION; }
+const char *svgt_pack_last_error(void) { return g_err; }
+
+int svgt_bam_open(const char *bam_path, const char *bai_path, svgt_bam_t **out)
+{
+    if (!bam_path || !out) return fail(SVGT_PACK_ERR_ARG, "null argument");
+    *out = nullptr;
+    svgt_bam *h = new (std::nothrow) svgt_bam();
+    if (!h) return fail(SVGT_PACK_ERR_IO, "out of memory");
+    svgt_bam_impl &B = h->impl;
+    B.sh = std::make_shared<Shared>();
+    Shared &S = *B.sh;
+    S.path = bam_path;
+    auto bail = [&](int code, const char *msg) { delete h; return fail(code, "%s: %s", msg, bam_path); };
+    if (!B.bgzf.open(bam_path)) return bail(SVGT_PACK_ERR_IO, "cannot open");
+    if (!B.bgzf.seek(0)) return bail(SVGT_PACK_ERR_IO, "not a BGZF file");
+    uint8_t w[8];
+    if (B.bgzf.read(w, 8) != 8 || memcmp(w, "BAM\1", 4) != 0) return bail(SVGT_PACK_ERR_IO, "not a BAM file");
+    const uint32_t l_text = rd32(w + 4);
+    std::vector<uint8_t> text(l_text);
+    if (l_text && B.bgzf.read(text.data(), l_text) != (long)l_text) return bail(SVGT_PACK_ERR_IO, "truncated header");
+    if (B.bgzf.read(w, 4) != 4) return bail(SVGT_PACK_ERR_IO, "truncated header");
+    const int n_ref = (int)rd32(w);
+    for (int i = 0; i < n_ref; ++i) {
+        if (B.bgzf.read(w, 4) != 4) return bail(SVGT_PACK_ERR_IO, "truncated reference list");
+        const uint32_t l_name = rd32(w);
+        std::vector<uint8_t> nm(l_name + 4);
+        if (l_name == 0 || l_name > 65536 || B.bgzf.read(nm.data(), l_name + 4) != (long)(l_name + 4))
+            return bail(SVGT_PACK_ERR_IO, "truncated reference list");
+        S.ref_names.emplace_back((const char *)nm.data(), l_name - 1);
+        S.ref_lens.push_back((int32_t)rd32(nm.data() + l_name));
+        S.tid_of[S.ref_names.back()] = i;         /* a repeated name keeps its last index, like the dict the Python reader builds */
+    }
+    S.first_record = B.bgzf.tell();
+    std::string cand[2];
+    if (bai_path) cand[0] = bai_path;
+    else {
+        cand[0] = std::string(bam_path) + ".bai";
+        std::string stem(bam_path);
+        const size_t dot = stem.rfind('.'), slash = stem.rfind('/');
+        if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) stem.resize(dot);
+        cand[1] = stem + ".bai";
+    }
+    bool ok = false;
+    for (auto &c : cand) if (!c.empty() && S.bai.load(c.c_str())) { ok = true; break; }
+    if (!ok) return bail(SVGT_PACK_ERR_IO, "no readable .bai index for");
+    *out = h;
+    return SVGT_PACK_OK;
+}
+
+int svgt_bam_close(svgt_bam_t *bam)
+{
+    delete bam;
+    return SVGT_PACK_OK;
+}
+
+int svgt_bam_n_references(const svgt_bam_t *bam) { return bam ? (int)bam->impl.sh->ref_names.size() : SVGT_PACK_ERR_ARG; }
+
+const char *svgt_bam_reference_name(const svgt_bam_t *bam, int tid)
+{
+    if (!bam || tid < 0 || tid >= (int)bam->impl.sh->ref_names.size()) return nullptr;
+    return bam->impl.sh->ref_names[tid].c_str();
+}
+
+int64_t svgt_bam_reference_length(const svgt_bam_t *bam, int tid)
+{
+    if (!bam || tid < 0 || tid >= (int)bam->impl.sh->ref_lens.size()) return SVGT_PACK_ERR_ARG;
+    return bam->impl.sh->ref_lens[tid];
+}
+
+int64_t svgt_bam_count(svgt_bam_t *bam, int tid, int64_t beg, int64_t end, int filter_all)
+{
+    if (!bam) return fail(SVGT_PACK_ERR_ARG, "null bam");
+    return count_region(bam->impl, tid, beg, end, filter_all != 0);
+}
+
+int svgt_pack_sites(svgt_bam_t *bam, const svgt_pack_site_t *sites, int64_t n_sites, const char *const *rg_names,
+                    const int32_t *rg_lib, int32_t n_rg, const uint8_t *lib_active, int32_t n_lib, int32_t mode,
+                    int64_t max_reads, int32_t n_threads, svgt_pack_count_t *counts)
+{
+    if (!bam || n_sites < 0 || (n_sites && (!sites || !counts)) || n_rg < 0 || (n_rg && (!rg_names || !rg_lib)) ||
+        n_lib < 0 || (n_lib && !lib_active))
+        return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    if (mode != SVGT_PACK_MODE_SSO && mode != SVGT_PACK_MODE_CLASSIC) return fail(SVGT_PACK_ERR_ARG, "bad mode %d", mode);
+    svgt_bam_impl &B = bam->impl;
+    B.frags.clear(); B.splits.clear();
+    std::unordered_map<std::string, int> rgmap;
+    for (int i = 0; i < n_rg; ++i) if (rg_names[i]) rgmap[rg_names[i]] = rg_lib[i];
+    PackJob job{rgmap, lib_active, n_lib, mode, max_reads};
+
+    /* sites are independent: blocks of consecutive sites go to worker threads, each with its own reader
+     * (file handle + block cache); rows are stitched back in site order */
+    const int64_t kBlock = 16;
+    const int64_t n_blocks = (n_sites + kBlock - 1) / kBlock;
+    int nt = n_threads <= 0 ? (int)std::thread::hardware_concurrency() : n_threads;
+    if (nt < 1) nt = 1;
+    if ((int64_t)nt > n_blocks) nt = (int)(n_blocks < 1 ? 1 : n_blocks);
+    if (nt == 1) {
+        for (int64_t si = 0; si < n_sites; ++si) {
+            const int rc = pack_one_site(B, job, sites[si], counts[si], B.frags, B.splits);
+            if (rc < 0) return rc;
+        }
+        return SVGT_PACK_OK;
+    }
+    struct BlockOut { std::vector<int32_t> frags, splits; };
+    std::vector<BlockOut> outs((size_t)n_blocks);
+    std::atomic<int64_t> cursor(0);
+    std::atomic<int> first_err(0);
+    std::vector<std::string> errs((size_t)nt);
+    auto worker = [&](int w) {
+        svgt_bam_impl R;
+        R.sh = B.sh;
+        if (!R.bgzf.open(B.sh->path.c_str())) {
+            int z = 0;
+            if (first_err.compare_exchange_strong(z, SVGT_PACK_ERR_IO)) errs[w] = "cannot reopen " + B.sh->path;
+            return;
+        }
+        for (;;) {
+            const int64_t b = cursor.fetch_add(1);
+            if (b >= n_blocks || first_err.load() != 0) return;
+            for (int64_t si = b * kBlock; si < std::min(n_sites, (b + 1) * kBlock); ++si) {
+                const int rc = pack_one_site(R, job, sites[si], counts[si], outs[b].frags, outs[b].splits);
+                if (rc < 0) {
+                    int z = 0;
+                    if (first_err.compare_exchange_strong(z, rc)) errs[w] = g_err;    /* g_err is thread-local */
+                    return;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nt; ++w) pool.emplace_back(worker, w);
+    for (auto &t : pool) t.join();
+    if (first_err.load() != 0) {
+        for (auto &e : errs) if (!e.empty()) return fail(first_err.load(), "%s", e.c_str());
+        return fail(first_err.load(), "worker failed");
+    }
+    size_t nf = 0, ns = 0;
+    for (auto &o : outs) { nf += o.frags.size(); ns += o.splits.size(); }
+    B.frags.reserve(nf); B.splits.reserve(ns);
+    for (auto &o : outs) {
+        B.frags.insert(B.frags.end(), o.frags.begin(), o.frags.end());
+        B.splits.insert(B.splits.end(), o.splits.begin(), o.splits.end());
+    }
+    return SVGT_PACK_OK;
+}
+
+int svgt_pack_rows(const svgt_bam_t *bam, const int32_t **frags, int64_t *n_frag, const int32_t **splits,
+                   int64_t *n_split)
+{
+    if (!bam || !frags || !n_frag || !splits || !n_split) return fail(SVGT_PACK_ERR_ARG, "null argument");
+    *frags = bam->impl.frags.data(); *n_frag = (int64_t)(bam->impl.frags.size() / 8);
+    *splits = bam->impl.splits.data(); *n_split = (int64_t)(bam->impl.splits.size() / 8);
+    return SVGT_PACK_OK;
+}
+
+}  // extern "C"

@@ -108,10 +108,22 @@ def warn(msg):
     sys.stderr.write(msg)
 
 
-def pack_sample(sample, plan, gather, min_aligned):
-    """Gather + pack every planned site of one sample into an EvidenceBatch."""
+def pack_sample_python(sample, plan, gather, min_aligned):
+    """Gather + pack every planned site of one sample into an EvidenceBatch (Python path: the parity
+    checker of the native packer, and the route for inputs the native reader does not open)."""
     packer = ev.BatchPacker(sample.bam.gettid, sample.library_table())
     for bp in plan.breakpoints:
         fragments, too_many = gather(sample, bp)
         packer.add_site(bp, fragments, skip=too_many)
     return packer.finish()
+
+
+def pack_sample(sample, plan, gather, min_aligned, mode=None, max_reads=None):
+    """Gather + pack every planned site of one sample.  With `mode` (packer.MODE_SSO / MODE_CLASSIC)
+    and an indexed .bam on disk the native packer (libsvgt_pack.so) does it in one call; otherwise the
+    Python gather `gather(sample, breakpoint)` runs per site."""
+    if mode is not None:
+        from . import packer as native_packer
+        if native_packer.usable(sample):
+            return native_packer.pack_sample(sample, plan, mode, max_reads, Z)
+    return pack_sample_python(sample, plan, gather, min_aligned)

@@ -1,0 +1,205 @@
+"""ctypes front-end of the native evidence packer (libsvgt_pack.so, include/svgt_pack.h).
+
+`pack_sample(sample, plan, mode, max_reads)` is the native twin of
+`genotype.pack_sample` (gather.gather_sso / gather.gather_classic + evidence.BatchPacker): one C
+call gathers the reads around every planned breakpoint of a BAM (BGZF + BAI reader, the pysam
+semantics of SURVEY.md 8c), groups them into fragments, runs the split-candidate QC and emits the
+32-byte fragment / split rows the scoring kernel streams.  The Python path stays as its parity
+checker (tests/test_pack_native.py) and serves inputs the native reader does not open (CRAM, a
+pysam handle without a .bai).
+
+Reference: gather_reads svtyper/classic.py:54-100, svtyper/singlesample.py:139-205;
+SamFragment.add_read svtyper/parsers.py:748-768; SplitRead.is_valid svtyper/parsers.py:959-1058.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from . import evidence as ev
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "svgt_pack.cpp")
+HEADER = os.path.join(HERE, "..", "include", "svgt_pack.h")
+LIB_PATH = os.path.join(HERE, "libsvgt_pack.so")
+
+MODE_SSO, MODE_CLASSIC = 0, 1
+OK, ERR_ARG, ERR_IO, ERR_RG, ERR_RECORD = 0, -1, -2, -3, -4
+
+_lib = None
+
+
+class PackError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "svgt_pack error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Site(ctypes.Structure):
+    _fields_ = [("tidA", ctypes.c_int32), ("begA", ctypes.c_int32), ("endA", ctypes.c_int32),
+                ("tidB", ctypes.c_int32), ("begB", ctypes.c_int32), ("endB", ctypes.c_int32)]
+
+
+class Count(ctypes.Structure):
+    _fields_ = [("n_frag_rows", ctypes.c_int32), ("n_split_rows", ctypes.c_int32),
+                ("skip", ctypes.c_int32), ("n_fragments", ctypes.c_int32)]
+
+
+def build(force=False):
+    """g++ -> svtyper_b200/libsvgt_pack.so (host code only, links zlib)."""
+    stale = (not os.path.exists(LIB_PATH) or
+             any(os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in (SRC, HEADER)))
+    if force or stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", LIB_PATH, SRC, "-lz", "-lpthread"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(LIB_PATH)
+        L.svgt_pack_abi_version.restype = ctypes.c_int
+        L.svgt_pack_last_error.restype = ctypes.c_char_p
+        L.svgt_bam_open.restype = ctypes.c_int
+        L.svgt_bam_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.svgt_bam_close.restype = ctypes.c_int
+        L.svgt_bam_close.argtypes = [ctypes.c_void_p]
+        L.svgt_bam_n_references.restype = ctypes.c_int
+        L.svgt_bam_n_references.argtypes = [ctypes.c_void_p]
+        L.svgt_bam_reference_name.restype = ctypes.c_char_p
+        L.svgt_bam_reference_name.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.svgt_bam_reference_length.restype = ctypes.c_int64
+        L.svgt_bam_reference_length.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.svgt_bam_count.restype = ctypes.c_int64
+        L.svgt_bam_count.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        L.svgt_pack_sites.restype = ctypes.c_int
+        L.svgt_pack_sites.argtypes = [ctypes.c_void_p, ctypes.POINTER(Site), ctypes.c_int64,
+                                      ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
+                                      ctypes.POINTER(ctypes.c_uint8), ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                      ctypes.c_int32, ctypes.POINTER(Count)]
+        L.svgt_pack_rows.restype = ctypes.c_int
+        L.svgt_pack_rows.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
+                                     ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
+                                     ctypes.POINTER(ctypes.c_int64)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise PackError(int(rc), lib().svgt_pack_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+class NativeBam(object):
+    """An indexed BAM opened by the native reader."""
+
+    def __init__(self, path, bai=None):
+        self._h = ctypes.c_void_p()
+        _check(lib().svgt_bam_open(os.fsencode(path), os.fsencode(bai) if bai else None, ctypes.byref(self._h)))
+        n = lib().svgt_bam_n_references(self._h)
+        self.references = tuple(lib().svgt_bam_reference_name(self._h, i).decode("ascii") for i in range(n))
+        self.lengths = tuple(int(lib().svgt_bam_reference_length(self._h, i)) for i in range(n))
+
+    def close(self):
+        if self._h:
+            lib().svgt_bam_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def count(self, tid, beg, end, read_callback="nofilter"):
+        return int(_check(lib().svgt_bam_count(self._h, tid, int(beg), int(end), 1 if read_callback == "all" else 0)))
+
+    def pack(self, sites, rg_names, rg_lib, lib_active, mode, max_reads, threads=0):
+        """sites: [(tidA, begA, endA, tidB, begB, endB)] -> (counts[n,4] int32, frags[n,8], splits[n,8])."""
+        n = len(sites)
+        arr = (Site * max(n, 1))(*[Site(*s) for s in sites])
+        counts = (Count * max(n, 1))()
+        names = (ctypes.c_char_p * max(len(rg_names), 1))(*[r.encode("ascii") for r in rg_names])
+        libs = (ctypes.c_int32 * max(len(rg_lib), 1))(*rg_lib)
+        active = (ctypes.c_uint8 * max(len(lib_active), 1))(*[1 if a else 0 for a in lib_active])
+        _check(lib().svgt_pack_sites(self._h, arr, n, names, libs, len(rg_names), active, len(lib_active), mode,
+                                     -1 if max_reads is None else int(max_reads), int(threads), counts))
+        fp, sp = ctypes.POINTER(ctypes.c_int32)(), ctypes.POINTER(ctypes.c_int32)()
+        nf, ns = ctypes.c_int64(), ctypes.c_int64()
+        _check(lib().svgt_pack_rows(self._h, ctypes.byref(fp), ctypes.byref(nf), ctypes.byref(sp), ctypes.byref(ns)))
+        frags = (np.ctypeslib.as_array(fp, shape=(nf.value, ev.FRAG_WORDS)).copy() if nf.value
+                 else np.zeros((0, ev.FRAG_WORDS), np.int32))
+        splits = (np.ctypeslib.as_array(sp, shape=(ns.value, ev.SPLIT_WORDS)).copy() if ns.value
+                  else np.zeros((0, ev.SPLIT_WORDS), np.int32))
+        cnt = np.frombuffer(counts, dtype=np.int32).reshape(-1, 4)[:n].copy()
+        return cnt, frags, splits
+
+
+def usable(sample):
+    """Can the native reader serve this sample?  (An indexed .bam on disk.)"""
+    if os.environ.get("SVGT_PACKER", "").lower() == "python":
+        return False
+    path = str(getattr(sample.bam, "filename", "") or "")
+    if isinstance(getattr(sample.bam, "filename", None), bytes):
+        path = sample.bam.filename.decode()
+    if not path.endswith(".bam") or not os.path.exists(path):
+        return False
+    return os.path.exists(path + ".bai") or os.path.exists(os.path.splitext(path)[0] + ".bai")
+
+
+def fetch_windows(sample, breakpoint, z, mode):
+    """The two fetch windows as the integers the BAM layer sees (reference classic.py:62-78,
+    singlesample.py:139-157): the flank arithmetic is fp64, the reader truncates."""
+    bam = sample.bam
+    flank = sample.fetch_flank(z)
+    out = []
+    for side in ("A", "B"):
+        end = breakpoint[side]
+        tid = bam.gettid(end["chrom"])
+        if tid < 0:
+            raise ValueError("invalid contig %r" % (end["chrom"],))
+        length = bam.lengths[tid]
+        lo = max(end["pos"] + end["ci"][0] - flank, 0)
+        hi = min(end["pos"] + end["ci"][1] + flank, length)
+        out.extend((tid, max(0, int(lo)), int(hi)))
+    return tuple(out)
+
+
+def pack_sample(sample, plan, mode, max_reads, z=3, threads=0):
+    """Native gather + pack of every planned site of one sample -> EvidenceBatch."""
+    path = sample.bam.filename.decode() if isinstance(sample.bam.filename, bytes) else str(sample.bam.filename)
+    nb = NativeBam(path)
+    try:
+        sites = [fetch_windows(sample, bp, z, mode) for bp in plan.breakpoints]
+        rg_names = list(sample.rg_to_lib.keys())
+        rg_lib = [sample.rg_to_lib[r] for r in rg_names]
+        n_lib = len(sample.libraries)
+        active = [i in sample.active for i in range(n_lib)]
+        cnt, frags, splits = nb.pack(sites, rg_names, rg_lib, active, mode, max_reads, threads)
+    finally:
+        nb.close()
+    rows = np.zeros((len(plan.breakpoints), ev.SITE_WORDS), dtype=np.int64)
+    f_off = s_off = 0
+    for i, bp in enumerate(plan.breakpoints):
+        A, B = bp["A"], bp["B"]
+        meta = ev.SVTYPE_CODE[bp["svtype"]]
+        if A["is_reverse"]:
+            meta |= ev.SITE_O1_REV
+        if B["is_reverse"]:
+            meta |= ev.SITE_O2_REV
+        n_f, n_s, skip = int(cnt[i, 0]), int(cnt[i, 1]), int(cnt[i, 2])
+        if skip:
+            meta |= ev.SITE_SKIP
+        rows[i] = (int(A["pos"]), int(B["pos"]), int(A["ci"][0]), int(A["ci"][1]), int(B["ci"][0]), int(B["ci"][1]),
+                   sites[i][0], sites[i][3], int(bp.get("var_length", 0) or 0), meta,
+                   f_off & 0xFFFFFFFF, f_off >> 32, n_f, s_off & 0xFFFFFFFF, s_off >> 32, n_s)
+        f_off += n_f
+        s_off += n_s
+    batch = ev.EvidenceBatch(rows.astype(np.int32), frags, splits, sample.library_table())
+    batch.order = batch.length_order()
+    return batch

@@ -11,7 +11,7 @@ import os
 import sys
 
 from . import evidence as ev
-from . import gather, genotype, vcf
+from . import gather, genotype, packer, vcf
 from .sample import SampleInfo, write_sample_json
 
 
@@ -86,7 +86,8 @@ def sso_genotype(bam_string,
             plan.site(rec, None, vcf.simple_breakpoint(rec, max_ci_dist))
 
     batch = genotype.pack_sample(
-        sample, plan, lambda smp, bp: gather.gather_sso(smp, bp, genotype.Z, max_reads), min_aligned)
+        sample, plan, lambda smp, bp: gather.gather_sso(smp, bp, genotype.Z, max_reads), min_aligned,
+        mode=packer.MODE_SSO, max_reads=max_reads)
     rows = genotype.score(batch, min_aligned=min_aligned, split_slop=genotype.SPLIT_SLOP,
                           split_weight=split_weight, disc_weight=disc_weight, assoc_mode=ev.ASSOC_SSO)
 
