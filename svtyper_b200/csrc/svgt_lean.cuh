@@ -179,7 +179,10 @@ __device__ __forceinline__ void fast_row(const int4 lo, const int4 hi, const int
  * names its own contig, and an INV pair may also straddle in the reciprocal orientation
  * (singlesample.py:296-303), whose windows are the alt windows shifted by -/+ FL.
  */
-__device__ __forceinline__ void fast_row_gen(const int4 lo, const int4 hi, const int4 f0, const int4 f1, const int4 f2,
+/* (inline on purpose: an out-of-line call here costs the one-contig loop 15 % -- measured -- through the
+ * registers it pins across the call) */
+__device__ __forceinline__
+void fast_row_gen(const int4 lo, const int4 hi, const int4 f0, const int4 f1, const int4 f2,
                                              const uint4 w0, const uint4 w1, double &hA, double &hB, double &wref,
                                              double &walt, int &tie)
 {
