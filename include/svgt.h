@@ -104,8 +104,8 @@ int svgt_launches_per_batch(const svgt_batch_t *batch);
  * per-lane cp.async.bulk (TMA 1-D) ring in shared memory; 2 / 3 = warp-cooperative (row per lane,
  * ordered sums interleaved over 8 / 4 sites per warp), tally + call kernels; 4 = warp-cooperative with
  * rows through a cp.async.bulk shared-memory ring; 5 = warp-cooperative with the lean row scorer and a
- * cp.async row ring (the default: 8 sites per work unit, 2 for batches too small to fill the GPU with
- * 8-site units); 6 / 7 = variant 5 pinned to 8 / 2 sites per unit.  -1 restores the default (or the
+ * cp.async row ring (the default: 8 sites per work unit after a 1-2-4 ramp that spreads the heaviest
+ * sites one per warp); 6 / 7 = variant 5 pinned to 8 / 2 sites per unit.  -1 restores the default (or the
  * SVGT_VARIANT environment variable).  Returns the variant now in force.  Variants 0-4 are kept as
  * parity cross-checks.
  */

@@ -23,7 +23,7 @@ enum {
     SVGT_VAR_COOP4 = 3,    /* warp-cooperative, 4 sites interleaved per warp                 */
     SVGT_VAR_RING = 4,     /* warp-cooperative, rows through a cp.async.bulk smem ring (svgt_ring.cu) */
     SVGT_VAR_LEAN = 5,     /* warp-cooperative with the lean row scorer (svgt_lean.cu), the default:
-                              8 sites per work unit, 2 for small batches                                     */
+                              8 sites per work unit after a 1-2-4 ramp over the heaviest sites            */
     SVGT_VAR_LEAN8 = 6,    /* the same, always 8 sites per unit (tests)                                     */
     SVGT_VAR_LEAN2 = 7,    /* the same, always 2 sites per unit (tests)                                     */
     SVGT_VAR_COUNT = 8
