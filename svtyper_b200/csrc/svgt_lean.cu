@@ -427,7 +427,7 @@ int launch_lean(const SvgtParams &p, bool ramp, cudaStream_t stream)
     /* the ramp trades a little replay efficiency on the heaviest ~7 W sites for a short critical path:
      * worth it until the batch is large enough to amortise its longest unit (measured: +2 % kernel time
      * at 1M sites, -30 % at 200k heavy-tailed sites) */
-    if (p.n_sites >= 64 * cap * kLeanWarps) ramp = false;
+    if (p.n_sites >= 256 * cap * kLeanWarps) ramp = false;      /* ~600k sites on a B200 */
     SvgtParams q = p;
     q.n_tiles = ramp ? 1 : 0;
     kern<<<grid, SVGT_LEAN_THREADS, smem, stream>>>(q);
