@@ -139,3 +139,106 @@ def test_entry_points_use_the_native_packer(sample, plan, monkeypatch):
     assert packer.usable(sample)
     monkeypatch.setenv("SVGT_PACKER", "python")
     assert not packer.usable(sample)
+
+
+# ---- constructed edge cases: a synthetic BAM read by both readers -------------------------------------
+def _synthetic_bam(tmp_path, seed):
+    """Reads around two breakends per site with everything the gather rules branch on: gapped reads
+    (D / N), soft and hard clips, SA tags (one / several entries, other contigs, unknown contig),
+    fragments with 1, 2 and 3+ primaries, duplicate / secondary / supplementary / unmapped records, a
+    repeated (name, flag) record, and an inactive library."""
+    import bamwriter
+    rng = np.random.default_rng(seed)
+    refs = [("chrA", 400000), ("chrB", 300000)]
+    header = ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chrA\tLN:400000\n@SQ\tSN:chrB\tLN:300000\n"
+              "@RG\tID:rg1\tSM:S1\tLB:libX\n@RG\tID:rg2\tSM:S1\tLB:libX\n@RG\tID:rg3\tSM:S1\tLB:libY\n")
+    sites, recs = [], []
+    cigars = ["100M", "60M5D40M", "30M200N70M", "20S80M", "75M25S", "10H90M", "40M2I58M", "15S60M3D10M15S",
+              "50M50H", "100M"]
+    for s in range(40):
+        posA = int(rng.integers(2000, 180000)) + 2000 * s
+        length = int(rng.integers(300, 6000))
+        inter = rng.random() < 0.2
+        tidB, posB = (1, int(rng.integers(2000, 250000))) if inter else (0, posA + length)
+        sites.append((0, posA, tidB, posB))
+        for f in range(int(rng.integers(3, 40))):
+            qname = "q%03d_%03d" % (s, int(rng.integers(0, 500)))          # collisions on purpose
+            n_prim = int(rng.choice([1, 2, 2, 2, 2, 3, 4]))
+            rg = str(rng.choice(["rg1", "rg2", "rg3"]))
+            for k in range(n_prim):
+                tid, anchor = (0, posA) if (k % 2 == 0 or rng.random() < 0.3) else (tidB, posB)
+                pos = max(0, anchor + int(rng.integers(-700, 700)))
+                flag = 0x1 | (0x10 if rng.random() < 0.5 else 0) | (0x40 if k == 0 else 0x80)
+                r = rng.random()
+                if r < 0.04:
+                    flag |= 0x400
+                elif r < 0.07:
+                    flag |= 0x100
+                elif r < 0.10:
+                    flag |= 0x800
+                elif r < 0.12:
+                    flag |= 0x4
+                cigar = str(rng.choice(cigars))
+                tags = [("RG", "Z", rg)]
+                r = rng.random()
+                if r < 0.25:
+                    sa_chr = str(rng.choice(["chrA", "chrA", "chrB", "chrUn"]))
+                    sa = "%s,%d,%s,%s,%d,0;" % (sa_chr, max(1, pos + int(rng.integers(-3000, 3000))),
+                                                rng.choice(["+", "-"]), rng.choice(["60S40M", "45M55S", "30S30M2D40M"]),
+                                                int(rng.integers(0, 61)))
+                    if rng.random() < 0.2:
+                        sa += "chrB,500,+,50M50S,20,1;"
+                    tags.append(("SA", "Z", sa))
+                tags.append(("NM", "i", int(rng.integers(0, 5))))
+                rec = dict(tid=tid, pos=pos, qname=qname, flag=flag, mapq=int(rng.integers(0, 61)), cigar=cigar,
+                           l_seq=int(rng.choice([0, 100])), tags=tags)
+                recs.append(rec)
+                if rng.random() < 0.05:
+                    recs.append(dict(rec))                                 # the same (name, flag) twice
+    recs.sort(key=lambda r: (r["tid"], r["pos"]))
+    path = str(tmp_path / ("synth%d.bam" % seed))
+    bamwriter.write_bam(path, refs, header, recs)
+    return path, sites
+
+
+class _Lib(object):
+    def __init__(self, name, rgs, mean, sd, prevalence):
+        self.name, self.readgroups, self.mean, self.sd, self.prevalence = name, rgs, mean, sd, prevalence
+        self.hist = {int(mean) + d: 10 for d in range(-50, 51)}
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_constructed_edge_cases_match_python_gather(tmp_path, seed):
+    from svtyper_b200.sample import SampleInfo
+    path, sites = _synthetic_bam(tmp_path, seed)
+    bam = bamio.AlignmentFile(path)
+    libs = [_Lib("libX", ["rg1", "rg2"], 300.0, 40.0, 0.9), _Lib("libY", ["rg3"], 420.0, 60.0, 0.9)]
+    for inactive in (False, True):
+        if inactive:
+            libs[1].prevalence = 1e-9                                    # below MIN_LIB_PREVALENCE: ignored
+        smp = SampleInfo("S1", bam, libs, 0, 0)
+        plan = genotype.SitePlan()
+        for tidA, posA, tidB, posB in sites:
+            bp = {"id": "x", "svtype": "BND" if tidB != tidA else "DEL", "var_length": posB - posA,
+                  "A": {"chrom": bam.references[tidA], "pos": posA, "ci": [-5, 7], "is_reverse": False},
+                  "B": {"chrom": bam.references[tidB], "pos": posB, "ci": [0, 0], "is_reverse": True}}
+            plan.breakpoints.append(bp)
+        for mode, mr in ((packer.MODE_SSO, None), (packer.MODE_SSO, 25), (packer.MODE_CLASSIC, None),
+                         (packer.MODE_CLASSIC, 18)):
+            if mode == packer.MODE_SSO:
+                g = lambda s_, bp_: gather.gather_sso(s_, bp_, genotype.Z, mr)
+            else:
+                g = lambda s_, bp_: gather.gather_classic(s_, bp_, genotype.Z, mr)
+            want = genotype.pack_sample_python(smp, plan, g, 20)
+            got = packer.pack_sample(smp, plan, mode, mr, genotype.Z, threads=3)
+            where = "seed %d mode %d max_reads %s inactive %s" % (seed, mode, mr, inactive)
+            assert np.array_equal(got.sites, want.sites), where
+            assert np.array_equal(got.frags, want.frags), where
+            assert np.array_equal(got.splits, want.splits), where
+            if mr is None:
+                fl = got.frags[:, 7]
+                assert (fl & ev.F_CONT).any() and (fl & ev.F_EXTRA).any() and (fl & ev.F_PAIRED).any(), where
+                assert got.n_split > 0 and ((got.splits[:, 6] >> 16) & ev.S_SOFT_CLIP).any(), where
+            else:
+                assert (got.sites[:, 9] & ev.SITE_SKIP).any(), where
+    bam.close()
