@@ -30,6 +30,9 @@ namespace {
 #define SVGT_LEAN_DEPTH 3           /* chunks in flight per warp (1 KB each) */
 #endif
 constexpr int kD = SVGT_LEAN_DEPTH;
+#ifndef SVGT_LEAN_TMA
+#define SVGT_LEAN_TMA 0             /* 1: one cp.async.bulk (TMA 1-D) per chunk on an mbarrier instead of per-lane cp.async */
+#endif
 constexpr int kLeanWarps = SVGT_LEAN_THREADS / 32;
 constexpr int kHistPad = 8;         /* sentinels behind the cached libraries' counts */
 constexpr int kLeanHistWords = 4864;/* shared-memory budget for the cached counts (the CTA uses ~211 KB besides) */
@@ -40,6 +43,7 @@ struct alignas(16) Strm { const int4 *rows; int n; int pad; };
 template <int G>
 struct alignas(128) LeanSmem {
     unsigned char ring[kD][1024];   /* cp.async targets: 32 x 16 B low halves, then 32 x 16 B high halves */
+    unsigned long long bar[kD];     /* SVGT_LEAN_TMA: one mbarrier per ring slot */
     Strm strm[2][8];                /* row streams: [0] fragment rows, [1] split rows (a chunk's low 4 bits index it) */
     SiteS site[G];
     SiteF sf[G];
@@ -140,6 +144,11 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
     for (long long i = tid; i < p.n_hist; i += SVGT_LEAN_THREADS) big |= p.hist[i] >= (1u << 26);
     WS &ws = s_warp[warp];
     if (lane < 2) ws.zero[lane] = 0.0;
+#if SVGT_LEAN_TMA
+    if (lane < kD) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lean_smem_addr(&ws.bar[lane])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned cc = 0u;                                       /* chunks consumed by this warp so far (slot phase) */
+#endif
     const bool small_counts = __syncthreads_or(big) == 0;
     /* lean copies of the first kWLibs histograms, each followed by a zero sentinel */
     if (tid == 0) {
@@ -180,6 +189,8 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
     const long long W = (long long)gridDim.x * kLeanWarps;
     const long long n_units = lean_n_units<G>(p.n_sites, W, ramp);
 
+    unsigned head = 0u;                                     /* ring slot of the chunk being scored; never reset, so
+                                                               slot s is always chunk number == s (mod kD) of this warp */
     long long unit = 0, unit_next = 0;
     if (lane == 0) unit = (long long)atomicAdd(reinterpret_cast<unsigned *>(p.status + 1), 1u);
     unit = __shfl_sync(full, unit, 0);
@@ -275,8 +286,31 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 it_mask &= it_mask - 1u;
                 return (it_step << 4) | it_phase | g;
             };
-            const unsigned ring = lean_smem_addr(&ws.ring[0][0]) + lane * 16;
             const Strm *strm = &ws.strm[0][0];
+#if SVGT_LEAN_TMA
+            const unsigned ring = lean_smem_addr(&ws.ring[0][0]) + lane * 32;
+            const unsigned bars = lean_smem_addr(&ws.bar[0]);
+            auto issue = [&](const int d, const unsigned slot) {
+                if (d >= 0) {
+                    const Strm q = strm[d & 15];
+                    const int row0 = (d >> 4) * 32;
+                    const int n = min(32, q.n - row0);
+                    const unsigned dst = ring + slot * 1024u;
+                    if (lane == 0) {
+                        const unsigned bytes = (unsigned)n * 32u;
+                        const unsigned bar = bars + slot * 8u;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst), "l"(q.rows + 2 * (long long)row0), "r"(bytes), "r"(bar) : "memory");
+                    }
+                    if (lane >= n) {                        /* rows beyond the last one read as zeros */
+                        asm volatile("st.shared.v4.s32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+                        asm volatile("st.shared.v4.s32 [%0], {%1, %1, %1, %1};" ::"r"(dst + 16u), "r"(0) : "memory");
+                    }
+                }
+            };
+#else
+            const unsigned ring = lean_smem_addr(&ws.ring[0][0]) + lane * 16;
             auto issue = [&](const int d, const unsigned slot) {
                 if (d >= 0) {
                     const Strm q = strm[d & 15];
@@ -291,22 +325,37 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
+#endif
             /* descriptors of the chunk being scored (dq[0]) and of the kD chunks in flight behind it */
             int dq[kD + 1];
-            unsigned head = 0u;                     /* ring slot of dq[0] */
 #pragma unroll
             for (int i = 0; i < kD; ++i) {
                 dq[i] = next_chunk();
-                issue(dq[i], (unsigned)i);
+                issue(dq[i], (head + (unsigned)i) % (unsigned)kD);
             }
             while (dq[0] >= 0) {
                 const int d = dq[0];
-                asm volatile("cp.async.wait_group %0;" ::"n"(kD - 1) : "memory");
                 const unsigned src = ring + head * 1024u;
                 int4 lo, hi;
+#if SVGT_LEAN_TMA
+                {
+                    const unsigned bar = bars + head * 8u, parity = (cc / (unsigned)kD) & 1u;
+                    unsigned ok;
+                    do {
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                    } while (!ok);
+                    ++cc;
+                }
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(src));
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                             : "r"(src + 16u));
+#else
+                asm volatile("cp.async.wait_group %0;" ::"n"(kD - 1) : "memory");
                 asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(src));
                 asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                              : "r"(src + 512u));
+#endif
                 /* refill the slot just read with the chunk kD ahead */
                 dq[kD] = next_chunk();
                 issue(dq[kD], head);

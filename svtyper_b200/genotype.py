@@ -40,21 +40,15 @@ def score(batch, **params):
     return _engine.score_host(batch, **params)
 
 
-def _set_counts(call, row):
-    for key in COUNT_FIELDS:
-        call.set(key, int(row[key]))
+def _count_items(row):
+    items = [(key, int(row[key])) for key in COUNT_FIELDS]
     total = int(row["QR"]) + int(row["QA"])
-    call.set("AB", "%.2g" % (int(row["QA"]) / float(total)) if total else ".")
+    items.append(("AB", "%.2g" % (int(row["QA"]) / float(total)) if total else "."))
+    return items
 
 
-def _set_blank(call):
-    call.set("GT", "./.")
-    call.set("GQ", ".")
-    call.set("SQ", ".")
-    call.set("GL", ".")
-    for key in ("DP", "AO", "RO", "AS", "ASC", "RS", "AP", "RP", "QR", "QA"):
-        call.set(key, 0)
-    call.set("AB", ".")
+_BLANK_ITEMS = ([("GT", "./."), ("GQ", "."), ("SQ", "."), ("GL", ".")] +
+                [(key, 0) for key in ("DP", "AO", "RO", "AS", "ASC", "RS", "AP", "RP", "QR", "QA")] + [("AB", ".")])
 
 
 def apply_row(rec, sample_name, row, classic):
@@ -63,7 +57,7 @@ def apply_row(rec, sample_name, row, classic):
     classic=True follows classic.py:437-513 (a too-many-reads site only gets GT './.'; a site
     with no evidence resets QUAL to 0); classic=False follows bayesian_genotype +
     assign_genotype_to_variant (singlesample.py:406-473, :544-575), where every non-called
-    outcome is the blank row.
+    outcome is the blank row.  All fields of the row go in through one SampleCall.set_many().
     """
     call = rec.call(sample_name)
     gt = int(row["GT"])
@@ -73,20 +67,17 @@ def apply_row(rec, sample_name, row, classic):
     if gt in (GT_BLANK, GT_SKIPPED):
         if classic:
             rec.qual = 0
-        _set_blank(call)
+        call.set_many(_BLANK_ITEMS)
         return
-    call.set("GL", ",".join("%.0f" % x for x in row["GL"]))
-    _set_counts(call, row)
+    items = [("GL", ",".join("%.0f" % x for x in row["GL"]))] + _count_items(row)
     if gt == GT_UNDERFLOW:
-        call.set("GQ", ".")
-        call.set("SQ", ".")
-        call.set("GT", "./.")
+        items += [("GQ", "."), ("SQ", "."), ("GT", "./.")]
+        call.set_many(items)
         return
     sq = float(row["SQ"])
-    call.set("GQ", int(row["GQ"]))
-    call.set("SQ", sq)
+    items += [("GQ", int(row["GQ"])), ("SQ", sq), ("GT", GT_TEXT[gt])]
+    call.set_many(items)
     rec.qual += sq
-    call.set("GT", GT_TEXT[gt])
 
 
 class SitePlan(object):

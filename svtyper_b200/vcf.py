@@ -91,9 +91,19 @@ class VcfHeader(object):
         if any(m.id == str(id_) for m in table):
             return                      # first definition wins
         table.append(MetaLine(kind, id_, number, type_, desc))
+        self._format_ids = None
 
     def format_ids(self):
-        return [m.id for m in self.formats]
+        ids = getattr(self, "_format_ids", None)
+        if ids is None or len(ids) != len(self.formats):
+            ids = self._format_ids = [m.id for m in self.formats]
+            self._format_rank = {k: i for i, k in enumerate(ids)}
+        return ids
+
+    def format_rank(self):
+        """{FORMAT id: position in the header}: the order FORMAT keys are written in."""
+        self.format_ids()
+        return self._format_rank
 
     def info_ids(self):
         return [m.id for m in self.infos]
@@ -156,15 +166,33 @@ class SampleCall(object):
         self.set("GT", gt)
 
     def set(self, key, value):
-        order = self.record.header.format_ids()
-        if key not in order:
+        rank = self.record.header.format_rank()
+        if key not in rank:
             sys.stderr.write('Error: invalid FORMAT field, "' + key + '"\n')
             sys.exit(1)
         self.values[key] = value
         active = self.record.active_formats
         if key not in active:
             active.append(key)
-            active.sort(key=order.index)
+            active.sort(key=rank.__getitem__)
+
+    def set_many(self, items):
+        """set() for a list of (key, value) pairs with one ordering pass (the scored row of a site)."""
+        rank = self.record.header.format_rank()
+        active = self.record.active_formats
+        seen = set(active)
+        grew = False
+        for key, value in items:
+            if key not in rank:
+                sys.stderr.write('Error: invalid FORMAT field, "' + key + '"\n')
+                sys.exit(1)
+            self.values[key] = value
+            if key not in seen:
+                seen.add(key)
+                active.append(key)
+                grew = True
+        if grew:
+            active.sort(key=rank.__getitem__)
 
     def get(self, key):
         return self.values[key]
@@ -240,7 +268,8 @@ class VcfRecord(object):
         return ";".join(parts)
 
     def format_string(self):
-        return ":".join(f for f in self.header.format_ids() if f in self.active_formats)
+        active = set(self.active_formats)
+        return ":".join(f for f in self.header.format_ids() if f in active)
 
     def render(self):
         calls = "\t".join(self.calls[s].render() for s in self.header.samples)
