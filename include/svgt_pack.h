@@ -82,6 +82,24 @@ int svgt_pack_sites(svgt_bam_t *bam, const svgt_pack_site_t *sites, int64_t n_si
                     const uint8_t *lib_active, int32_t n_lib, int32_t mode, int64_t max_reads,
                     int32_t n_threads, svgt_pack_count_t *counts);
 
+/*
+ * Library statistics inputs in ONE pass over the head of the BAM, replacing the
+ * three per-library passes of Library.calc_read_length / calc_insert_hist / calc_lib_prevalence
+ * (svtyper/parsers.py:501-576): per library the longest query length among its first
+ * `read_length_reads` + 1 reads (reference: 10000), the template-length counts of its first `num_samp`
+ * forward reads with a mapped reverse mate (tlen > 0, primary), and its share of the first
+ * `prevalence_records` records (reference: 100000).  The median / MAD trimming and mean / sd stay in
+ * Python (sample.py), on the table fetched with svgt_bam_scan_hist() in first-seen key order.
+ */
+typedef struct svgt_lib_scan {
+    int64_t read_length, lib_records, records_seen, n_hist;
+} svgt_lib_scan_t;
+
+int svgt_bam_scan_libraries(svgt_bam_t *bam, const char *const *rg_names, const int32_t *rg_lib, int32_t n_rg,
+                            int32_t n_lib, int64_t num_samp, int64_t read_length_reads, int64_t prevalence_records,
+                            svgt_lib_scan_t *out);
+int svgt_bam_scan_hist(const svgt_bam_t *bam, int32_t lib, const int32_t **keys, const int64_t **counts, int64_t *n);
+
 /* Row buffers of the last svgt_pack_sites(): [n_frag][8] and [n_split][8] int32 words. */
 int svgt_pack_rows(const svgt_bam_t *bam, const int32_t **frags, int64_t *n_frag, const int32_t **splits,
                    int64_t *n_split);

@@ -237,7 +237,7 @@ struct Bai {
 /* one BAM record (what the gatherer keeps of it)                                               */
 /* ------------------------------------------------------------------------------------------ */
 struct Read {
-    int32_t tid = -1, pos = 0, end = 0, mapq = 0, flag = 0, l_seq = 0;
+    int32_t tid = -1, pos = 0, end = 0, mapq = 0, flag = 0, l_seq = 0, tlen = 0;
     std::string qname;
     std::vector<std::pair<int, int>> cigar;       /* (op, len) */
     std::string rg, sa;
@@ -293,11 +293,19 @@ struct Shared {
 };
 
 /* one reader: its own file handle, block cache and record buffer (one per worker thread) */
+/* insert-size table of one library in first-seen order (the order a Python dict would keep) */
+struct LibScan {
+    std::vector<int32_t> keys;
+    std::vector<int64_t> counts;
+    std::unordered_map<int32_t, size_t> slot;
+};
+
 struct svgt_bam_impl {
     Bgzf bgzf;
     std::shared_ptr<Shared> sh;
     std::vector<uint8_t> buf;
     std::vector<int32_t> frags, splits;               /* rows of the last svgt_pack_sites() */
+    std::vector<LibScan> scans;                       /* tables of the last svgt_bam_scan_libraries() */
 };
 
 /* next record at the reader's position: 1 = ok, 0 = end of file, -1 = corrupt */
@@ -318,6 +326,7 @@ int next_record(svgt_bam_impl &B, Read &r, bool want_tags)
     const unsigned n_cig = rd16(b + 12);
     r.flag = rd16(b + 14);
     r.l_seq = (int32_t)rd32(b + 16);
+    r.tlen = (int32_t)rd32(b + 28);
     size_t p = 32;
     if (p + l_name + 4 * (size_t)n_cig > sz || l_name == 0) return -1;
     r.qname.assign((const char *)b + p, l_name - 1);
@@ -834,6 +843,75 @@ int svgt_pack_sites(svgt_bam_t *bam, const svgt_pack_site_t *sites, int64_t n_si
         B.frags.insert(B.frags.end(), o.frags.begin(), o.frags.end());
         B.splits.insert(B.splits.end(), o.splits.begin(), o.splits.end());
     }
+    return SVGT_PACK_OK;
+}
+
+int svgt_bam_scan_libraries(svgt_bam_t *bam, const char *const *rg_names, const int32_t *rg_lib, int32_t n_rg,
+                            int32_t n_lib, int64_t num_samp, int64_t read_length_reads, int64_t prevalence_records,
+                            svgt_lib_scan_t *out)
+{
+    if (!bam || n_rg < 0 || (n_rg && (!rg_names || !rg_lib)) || n_lib <= 0 || !out)
+        return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    svgt_bam_impl &B = bam->impl;
+    std::unordered_map<std::string, int> rgmap;
+    for (int i = 0; i < n_rg; ++i) if (rg_names[i] && rg_lib[i] >= 0 && rg_lib[i] < n_lib) rgmap[rg_names[i]] = rg_lib[i];
+    B.scans.assign((size_t)n_lib, LibScan());
+    struct St { int64_t rl_seen = 0, longest = 0, taken = 0, mine = 0; bool rl_done = false, ins_done = false; };
+    std::vector<St> st((size_t)n_lib);
+    for (auto &s : st) { s.ins_done = num_samp <= 0; }
+    int64_t seen = 0;                                 /* records examined by the prevalence pass */
+    if (!B.bgzf.seek(B.sh->first_record)) return fail(SVGT_PACK_ERR_IO, "BGZF seek failed");
+    Read r;
+    for (;;) {
+        bool all_done = seen >= prevalence_records;
+        for (auto &s : st) all_done = all_done && s.rl_done && s.ins_done;
+        if (all_done) break;
+        const int rc = next_record(B, r, true);
+        if (rc < 0) return fail(SVGT_PACK_ERR_IO, "corrupt BAM record");
+        if (rc == 0 || r.tid < 0) break;              /* fetch() without a region stops at the unplaced reads */
+        if (!r.has_rg) return fail(SVGT_PACK_ERR_RG, "read %s has no RG tag", r.qname.c_str());
+        auto it = rgmap.find(r.rg);
+        const int lib = it == rgmap.end() ? -1 : it->second;
+        if (seen < prevalence_records) {              /* Library.calc_lib_prevalence, parsers.py:555-576 */
+            if (lib >= 0) ++st[lib].mine;
+            ++seen;
+        }
+        if (lib < 0) continue;
+        St &s = st[lib];
+        if (!s.rl_done) {                             /* Library.calc_read_length, parsers.py:501-516 */
+            int64_t n = 0;
+            for (auto &c : r.cigar) if (c.first == 0 || c.first == 1 || c.first == 4 || c.first == 7 || c.first == 8) n += c.second;
+            if (n > s.longest) s.longest = n;
+            if (s.rl_seen == read_length_reads) s.rl_done = true;
+            else ++s.rl_seen;
+        }
+        if (!s.ins_done) {                            /* Library.calc_insert_hist, parsers.py:518-553 */
+            const bool skip = (r.flag & 0x10) || !(r.flag & 0x20) || (r.flag & 0x4) || (r.flag & 0x8) ||
+                              (r.flag & FSUPPLEMENTARY) || (r.flag & FSECONDARY) || r.tlen <= 0;
+            if (!skip) {
+                LibScan &L = B.scans[lib];
+                auto f = L.slot.find(r.tlen);
+                if (f == L.slot.end()) { L.slot.emplace(r.tlen, L.keys.size()); L.keys.push_back(r.tlen); L.counts.push_back(1); }
+                else ++L.counts[f->second];
+                if (++s.taken == num_samp) s.ins_done = true;
+            }
+        }
+    }
+    for (int l = 0; l < n_lib; ++l) {
+        out[l].read_length = st[l].longest;
+        out[l].lib_records = st[l].mine;
+        out[l].records_seen = seen;
+        out[l].n_hist = (int64_t)B.scans[l].keys.size();
+    }
+    return SVGT_PACK_OK;
+}
+
+int svgt_bam_scan_hist(const svgt_bam_t *bam, int32_t lib, const int32_t **keys, const int64_t **counts, int64_t *n)
+{
+    if (!bam || !keys || !counts || !n || lib < 0 || lib >= (int)bam->impl.scans.size())
+        return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    const LibScan &L = bam->impl.scans[lib];
+    *keys = L.keys.data(); *counts = L.counts.data(); *n = (int64_t)L.keys.size();
     return SVGT_PACK_OK;
 }
 

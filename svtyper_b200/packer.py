@@ -48,6 +48,11 @@ class Count(ctypes.Structure):
                 ("skip", ctypes.c_int32), ("n_fragments", ctypes.c_int32)]
 
 
+class LibScan(ctypes.Structure):
+    _fields_ = [("read_length", ctypes.c_int64), ("lib_records", ctypes.c_int64),
+                ("records_seen", ctypes.c_int64), ("n_hist", ctypes.c_int64)]
+
+
 def build(force=False):
     """g++ -> svtyper_b200/libsvgt_pack.so (host code only, links zlib)."""
     stale = (not os.path.exists(LIB_PATH) or
@@ -81,6 +86,13 @@ def lib():
                                       ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
                                       ctypes.POINTER(ctypes.c_uint8), ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                       ctypes.c_int32, ctypes.POINTER(Count)]
+        L.svgt_bam_scan_libraries.restype = ctypes.c_int
+        L.svgt_bam_scan_libraries.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p),
+                                              ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(LibScan)]
+        L.svgt_bam_scan_hist.restype = ctypes.c_int
+        L.svgt_bam_scan_hist.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
+                                         ctypes.POINTER(ctypes.POINTER(ctypes.c_int64)), ctypes.POINTER(ctypes.c_int64)]
         L.svgt_pack_rows.restype = ctypes.c_int
         L.svgt_pack_rows.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
@@ -140,16 +152,52 @@ class NativeBam(object):
         return cnt, frags, splits
 
 
-def usable(sample):
-    """Can the native reader serve this sample?  (An indexed .bam on disk.)"""
+def _path_of(bam):
+    name = getattr(bam, "filename", "") or ""
+    return name.decode() if isinstance(name, bytes) else str(name)
+
+
+def usable_path(bam):
+    """Can the native reader open this alignment file?  (An indexed .bam on disk.)"""
     if os.environ.get("SVGT_PACKER", "").lower() == "python":
         return False
-    path = str(getattr(sample.bam, "filename", "") or "")
-    if isinstance(getattr(sample.bam, "filename", None), bytes):
-        path = sample.bam.filename.decode()
+    path = _path_of(bam)
     if not path.endswith(".bam") or not os.path.exists(path):
         return False
     return os.path.exists(path + ".bai") or os.path.exists(os.path.splitext(path)[0] + ".bai")
+
+
+def usable(sample):
+    """Can the native reader serve this sample?"""
+    return usable_path(sample.bam)
+
+
+def scan_libraries(bam, readgroups_per_lib, num_samp, read_length_reads=10000, prevalence_records=100000):
+    """One native pass over the head of the BAM -> [(read_length, lib_records, records_seen,
+    {template length: count} in first-seen order)] per library (reference parsers.py:501-576)."""
+    nb = NativeBam(_path_of(bam))
+    try:
+        names, libs = [], []
+        for i, groups in enumerate(readgroups_per_lib):
+            for g in groups:
+                names.append(g.encode("ascii"))
+                libs.append(i)
+        n_lib = len(readgroups_per_lib)
+        c_names = (ctypes.c_char_p * max(len(names), 1))(*names)
+        c_libs = (ctypes.c_int32 * max(len(libs), 1))(*libs)
+        out = (LibScan * max(n_lib, 1))()
+        _check(lib().svgt_bam_scan_libraries(nb._h, c_names, c_libs, len(names), n_lib, int(num_samp),
+                                             int(read_length_reads), int(prevalence_records), out))
+        res = []
+        for i in range(n_lib):
+            kp, cp = ctypes.POINTER(ctypes.c_int32)(), ctypes.POINTER(ctypes.c_int64)()
+            n = ctypes.c_int64()
+            _check(lib().svgt_bam_scan_hist(nb._h, i, ctypes.byref(kp), ctypes.byref(cp), ctypes.byref(n)))
+            hist = {int(kp[j]): int(cp[j]) for j in range(n.value)}
+            res.append((int(out[i].read_length), int(out[i].lib_records), int(out[i].records_seen), hist))
+        return res
+    finally:
+        nb.close()
 
 
 def fetch_windows(sample, breakpoint, z, mode):

@@ -130,6 +130,10 @@ class LibraryInfo(object):
             taken += 1
             if taken == num_samp:
                 break
+        self._finish_hist(hist, bam)
+
+    def _finish_hist(self, hist, bam):
+        """Outlier trimming + moments of the raw {template length: count} table (parsers.py:536-553)."""
         if not hist:
             sys.stderr.write("Error: failed to build insert size histogram for paired-end reads.\n"
                              "Please ensure BAM file (%s) has inward facing, paired-end reads.\n" % bam.filename)
@@ -188,13 +192,34 @@ class SampleInfo(object):
         return cls(name, bam, list(by_name.values()), entry["mapped"], entry["unmapped"])
 
     @classmethod
-    def from_bam(cls, bam, num_samp):
+    def from_bam(cls, bam, num_samp, native=None):
+        """Libraries measured from the BAM.  With an indexed .bam on disk the three passes per library
+        (read length, insert sizes, prevalence) are one native scan (libsvgt_pack.so,
+        svgt_bam_scan_libraries); `native=False` forces the Python passes (its parity checker)."""
         name = bam.header["RG"][0]["SM"]
         by_name = OrderedDict()
         for rg in bam.header["RG"]:
             lib_name = rg.get("LB", "")
             if lib_name not in by_name:
-                by_name[lib_name] = LibraryInfo.from_bam(bam, lib_name, num_samp)
+                by_name[lib_name] = None
+        if native is None:
+            from . import packer
+            native = packer.usable_path(bam)
+        if native:
+            from . import packer
+            libs = []
+            for lib_name in by_name:
+                groups = [rg["ID"] for rg in bam.header["RG"]
+                          if ((rg["LB"] == lib_name) if "LB" in rg else (lib_name == ""))]
+                libs.append(LibraryInfo(lib_name, groups, None, None, None, None, None))
+            scans = packer.scan_libraries(bam, [lib.readgroups for lib in libs], num_samp)
+            for lib, (read_length, mine, seen, hist) in zip(libs, scans):
+                lib.read_length = read_length
+                lib._finish_hist(hist, bam)
+                lib.prevalence = float(mine) / seen
+            return cls(name, bam, libs, bam.mapped, bam.unmapped)
+        for lib_name in by_name:
+            by_name[lib_name] = LibraryInfo.from_bam(bam, lib_name, num_samp)
         return cls(name, bam, list(by_name.values()), bam.mapped, bam.unmapped)
 
     @classmethod

@@ -34,13 +34,13 @@ def _parse_cigar(text):
     return out
 
 
-def encode_record(tid, pos, qname, flag, mapq, cigar, l_seq, tags):
+def encode_record(tid, pos, qname, flag, mapq, cigar, l_seq, tags, tlen=0):
     """tags: list of (key, 'Z'|'i'|'A', value)."""
     cig = _parse_cigar(cigar) if isinstance(cigar, str) else list(cigar)
     end = pos + sum(n for op, n in cig if op in (0, 2, 3, 7, 8))
     name = qname.encode("ascii") + b"\x00"
     body = struct.pack("<iiBBHHHiiii", tid, pos, len(name), mapq, _reg2bin(pos, max(end, pos + 1)), len(cig), flag,
-                       l_seq, -1, -1, 0)
+                       l_seq, -1, -1, tlen)
     body += name + b"".join(struct.pack("<I", (n << 4) | op) for op, n in cig)
     body += b"\x00" * ((l_seq + 1) // 2) + b"\xff" * l_seq
     for key, typ, val in tags:
@@ -79,7 +79,7 @@ def write_bam(path, references, header_text, records, block_bytes=3000):
         cur, cur_recs = b"", []
     for rec in records:
         enc, end = encode_record(rec["tid"], rec["pos"], rec["qname"], rec["flag"], rec["mapq"], rec["cigar"],
-                                 rec.get("l_seq", 0), rec.get("tags", []))
+                                 rec.get("l_seq", 0), rec.get("tags", []), rec.get("tlen", 0))
         if len(cur) + len(enc) > block_bytes:
             flush()
         cur += enc

@@ -96,6 +96,35 @@ def test_thread_count_does_not_change_the_rows(sample, plan):
         assert np.array_equal(many.splits, one.splits)
 
 
+@pytest.mark.parametrize("num_samp", [1000000, 5000, 37])
+def test_library_scan_matches_python_passes(num_samp):
+    """svgt_bam_scan_libraries (one pass) against the three Python passes per library, on the fixture
+    and on a constructed two-library BAM: same read length, prevalence, histogram (values AND key
+    order), hence the same mean / sd and the same -l JSON."""
+    import json
+    bam = bamio.AlignmentFile(BAM)
+    want = SampleInfo.from_bam(bam, num_samp, native=False)
+    got = SampleInfo.from_bam(bam, num_samp, native=True)
+    assert json.dumps(got.to_json()) == json.dumps(want.to_json())
+    for a, b in zip(got.libraries, want.libraries):
+        assert list(a.hist.items()) == list(b.hist.items()) and a.mean == b.mean and a.sd == b.sd
+        assert a.read_length == b.read_length and a.prevalence == b.prevalence and a.readgroups == b.readgroups
+    bam.close()
+
+
+def test_library_scan_two_libraries(tmp_path):
+    path, _ = _synthetic_bam(tmp_path, 11)
+    bam = bamio.AlignmentFile(path)
+    for num_samp in (100000, 50):
+        want = SampleInfo.from_bam(bam, num_samp, native=False)
+        got = SampleInfo.from_bam(bam, num_samp, native=True)
+        assert len(got.libraries) == 2
+        for a, b in zip(got.libraries, want.libraries):
+            assert list(a.hist.items()) == list(b.hist.items()) and (a.mean, a.sd) == (b.mean, b.sd)
+            assert (a.read_length, a.prevalence, a.name) == (b.read_length, b.prevalence, b.name)
+    bam.close()
+
+
 def test_count_matches_python_reader():
     nb = packer.NativeBam(BAM)
     pb = bamio.AlignmentFile(BAM)
@@ -190,8 +219,10 @@ def _synthetic_bam(tmp_path, seed):
                         sa += "chrB,500,+,50M50S,20,1;"
                     tags.append(("SA", "Z", sa))
                 tags.append(("NM", "i", int(rng.integers(0, 5))))
+                if rng.random() < 0.6:
+                    flag |= 0x20                                           # mate on the reverse strand
                 rec = dict(tid=tid, pos=pos, qname=qname, flag=flag, mapq=int(rng.integers(0, 61)), cigar=cigar,
-                           l_seq=int(rng.choice([0, 100])), tags=tags)
+                           l_seq=int(rng.choice([0, 100])), tags=tags, tlen=int(rng.integers(-200, 900)))
                 recs.append(rec)
                 if rng.random() < 0.05:
                     recs.append(dict(rec))                                 # the same (name, flag) twice
