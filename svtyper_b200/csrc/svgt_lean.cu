@@ -30,6 +30,9 @@ namespace {
 #define SVGT_LEAN_DEPTH 3           /* chunks in flight per warp (1 KB each) */
 #endif
 constexpr int kD = SVGT_LEAN_DEPTH;
+#ifndef SVGT_LEAN_CP
+#define SVGT_LEAN_CP "cp.async.cg.shared.global"        /* A/B: .ca (through L1), .L2::128B / .L2::256B prefetch hints */
+#endif
 #ifndef SVGT_LEAN_TMA
 #define SVGT_LEAN_TMA 0             /* 1: one cp.async.bulk (TMA 1-D) per chunk on an mbarrier instead of per-lane cp.async */
 #endif
@@ -319,9 +322,8 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                     const int4 *src = q.rows + 2 * (long long)min(row, q.n - 1);
                     const unsigned bytes = row < q.n ? 16u : 0u;
                     const unsigned dst = ring + slot * 1024u;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 512u), "l"(src + 1), "r"(bytes)
-                                 : "memory");
+                    asm volatile(SVGT_LEAN_CP " [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+                    asm volatile(SVGT_LEAN_CP " [%0], [%1], 16, %2;" ::"r"(dst + 512u), "l"(src + 1), "r"(bytes) : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
