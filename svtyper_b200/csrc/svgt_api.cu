@@ -86,6 +86,7 @@ int svgt_launches_per_batch(const svgt_batch_t *batch)
 {
     if (!batch) return fail(SVGT_ERR_ARG, "null batch%s", nullptr);
     if (batch->n_sites <= 0) return 0;
+    if (current_variant() >= SVGT_VAR_LEAN) return svgt_lean_launches();
     return current_variant() >= SVGT_VAR_COOP ? 2 : 1;      /* tally + call kernels, or one fused kernel */
 }
 

@@ -57,3 +57,4 @@ int svgt_launch_coop(const SvgtParams &p, int variant, cudaStream_t stream);
 int svgt_launch_call(const SvgtParams &p, cudaStream_t stream);
 int svgt_launch_ring(const SvgtParams &p, cudaStream_t stream);
 int svgt_launch_lean(const SvgtParams &p, int variant, cudaStream_t stream);
+int svgt_lean_launches(void);

@@ -30,6 +30,10 @@ namespace {
 #define SVGT_LEAN_DEPTH 3           /* chunks in flight per warp (1 KB each) */
 #endif
 constexpr int kD = SVGT_LEAN_DEPTH;
+#ifndef SVGT_LEAN_FUSE_CALL
+#define SVGT_LEAN_FUSE_CALL 0       /* 1: the genotype call runs at the end of each work unit (one launch): measured +26 % kernel time at 1M
+                                       sites (log_choose is a latency-bound loop; in svgt_call_kernel a million threads hide it), -16 % at 10k */
+#endif
 #ifndef SVGT_LEAN_CP
 #define SVGT_LEAN_CP "cp.async.cg.shared.global"        /* A/B: .ca (through L1), .L2::128B / .L2::256B prefetch hints */
 #endif
@@ -92,6 +96,29 @@ __device__ __forceinline__ unsigned lean_smem_addr(const void *p) { return (unsi
 __host__ __device__ __forceinline__ long long lean_hist_words(long long n_hist)
 {
     return (n_hist < kLeanHistWords ? n_hist : kLeanHistWords) + kHistPad;
+}
+
+/* the genotype call of one site on its five sums (what svgt_call_kernel does per thread), out of line */
+__device__ __noinline__ int finish_site(const SvgtParams &p, int site, int status, int svtype, double ref_seq,
+                                        double alt_seq, double alt_clip, double ref_span, double alt_span)
+{
+    svgt_out_row_t o;
+    o.gl[0] = o.gl[1] = o.gl[2] = 0.0; o.sq = 0.0;
+    o.gt = 0; o.gq = 0; o.dp = 0; o.ro = 0; o.ao = 0; o.qr = 0; o.qa = 0;
+    o.rs = 0; o.as_ = 0; o.asc = 0; o.rp = 0; o.ap = 0;
+    int e = 0;
+    if (status == 1) { o.gt = SVGT_GT_SKIPPED; o.gq = -1; }
+    else if (status == 2) { o.gt = SVGT_GT_BLANK; o.gq = -1; e = SVGT_ERR_RANGE; }
+    else {
+        Tables t;
+        t.pm = p.pm; t.libs = nullptr; t.hist = p.hist; t.conc = 0.0; t.disc = 0.0;
+        call_site(p, t, svtype, ref_seq, alt_seq, alt_clip, ref_span, alt_span, o, e);
+    }
+    int4 *dst = reinterpret_cast<int4 *>(p.out + site);
+    const int4 *src = reinterpret_cast<const int4 *>(&o);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = src[i];
+    return e;
 }
 
 /* non-fast sites: the cooperative kernel's scorer, out of line so the hot loop stays small; everything
@@ -228,6 +255,7 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 S.posA = a.x; S.posB = a.y; S.ciA0 = a.z; S.ciA1 = a.w; S.ciB0 = b.x; S.ciB1 = b.y;
                 S.dAB = a.y - a.x; S.nf = nf; S.foff = foff; S.soff = soff; S.ns = ns;
                 S.slot = valid ? (int)site : -1;        /* where the sums go (order[] is int32) */
+                S.pad1 = (meta & SITE_SKIP) ? 1 : (!ranged ? 2 : 0);     /* fused call: skipped / out of range */
                 SiteF &F = ws.sf[lane];
                 const int svtype = meta & 3;
                 F.tA = b.z; F.wA0 = a.x - m; F.wA1 = a.x + m; F.wB0 = a.y - m; F.wB1 = a.y + m;
@@ -415,8 +443,27 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
             sum_split = acc;
         }
 
+#if SVGT_LEAN_FUSE_CALL
+        /* ---- zeroing rules + bayesian_genotype (singlesample.py:382-473) for the unit's sites: lane 4g gathers
+         *      the five sums of site g and writes the final 80-byte row ---- */
+        {
+            const double ref_span = __shfl_down_sync(full, sum_frag, 1), alt_span = __shfl_down_sync(full, sum_frag, 2);
+            const double alt_clip = __shfl_down_sync(full, sum_split, 1);
+            if (gb < G && c == 0) {
+                const int site = ws.site[gb].slot;
+                if (site >= 0) {
+                    const int e = finish_site(p, site, ws.site[gb].pad1, ws.site[gb].meta & 3, sum_frag, sum_split, alt_clip,
+                                              ref_span, alt_span);
+                    if (e) err = e;
+                }
+            }
+        }
+        __syncwarp();
+        if (false) {
+#else
         /* ---- park the five sums in the site's output row (lane 4g+c holds chain c of site g) ---- */
         if (gb < G && c < 3) {
+#endif
             const int site = ws.site[gb].slot;
             if (site >= 0 && (ws.site[gb].nf | ws.site[gb].ns)) {
                 double *row = reinterpret_cast<double *>(p.out + site);
@@ -483,10 +530,16 @@ int launch_lean(const SvgtParams &p, bool ramp, cudaStream_t stream)
     q.n_tiles = ramp ? 1 : 0;
     kern<<<grid, SVGT_LEAN_THREADS, smem, stream>>>(q);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+#if SVGT_LEAN_FUSE_CALL
+    return 0;
+#else
     return svgt_launch_call(p, stream);
+#endif
 }
 
 }  // namespace
+
+int svgt_lean_launches(void) { return SVGT_LEAN_FUSE_CALL ? 1 : 2; }
 
 #ifndef SVGT_LEAN_G
 #define SVGT_LEAN_G 8
