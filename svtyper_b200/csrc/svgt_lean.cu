@@ -98,6 +98,7 @@ __host__ __device__ __forceinline__ long long lean_hist_words(long long n_hist)
     return (n_hist < kLeanHistWords ? n_hist : kLeanHistWords) + kHistPad;
 }
 
+#if SVGT_LEAN_FUSE_CALL
 /* the genotype call of one site on its five sums (what svgt_call_kernel does per thread), out of line */
 __device__ __noinline__ int finish_site(const SvgtParams &p, int site, int status, int svtype, double ref_seq,
                                         double alt_seq, double alt_clip, double ref_span, double alt_span)
@@ -120,6 +121,7 @@ __device__ __noinline__ int finish_site(const SvgtParams &p, int site, int statu
     for (int i = 0; i < 5; ++i) dst[i] = src[i];
     return e;
 }
+#endif
 
 /* non-fast sites: the cooperative kernel's scorer, out of line so the hot loop stays small; everything
  * the hot loop keeps in registers travels by value */
