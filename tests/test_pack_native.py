@@ -273,3 +273,46 @@ def test_constructed_edge_cases_match_python_gather(tmp_path, seed):
             else:
                 assert (got.sites[:, 9] & ev.SITE_SKIP).any(), where
     bam.close()
+
+
+def test_corrupted_files_never_crash(tmp_path):
+    """The native reader parses untrusted files: random byte flips / truncations of the fixture BAM and BAI
+    must end in a result or a PackError, never in a crash (run in a child process so a crash is visible)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, random, sys
+sys.path.insert(0, %r)
+from svtyper_b200 import packer
+src = %r
+bam = open(src, "rb").read(); bai = open(src + ".bai", "rb").read()
+random.seed(20261017)
+d = %r
+for it in range(60):
+    b, i = bytearray(bam), bytearray(bai)
+    mode = it %% 4
+    if mode == 0:
+        for _ in range(random.randint(1, 20)): b[random.randrange(len(b))] = random.randrange(256)
+    elif mode == 1:
+        b = b[:random.randrange(1, len(b))]
+    elif mode == 2:
+        for _ in range(random.randint(1, 20)): i[random.randrange(len(i))] = random.randrange(256)
+    else:
+        i = i[:random.randrange(1, len(i))]
+    p = os.path.join(d, "f.bam")
+    open(p, "wb").write(bytes(b)); open(p + ".bai", "wb").write(bytes(i))
+    try:
+        nb = packer.NativeBam(p)
+        sites = [(0, 1000000 * k %% 200000000, 1000000 * k %% 200000000 + 3000, 0, 5000 * k, 5000 * k + 2000) for k in range(1, 20)]
+        try:
+            nb.pack(sites, ["x"], [0], [True], it %% 2, None if it %% 3 else 50, threads=1 + it %% 3)
+            nb.count(0, 0, 250000000, "all")
+        except packer.PackError:
+            pass
+        nb.close()
+    except packer.PackError:
+        pass
+print("survived")
+''' % (REPO, BAM, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "survived" in r.stdout, (r.returncode, r.stderr[-500:])
