@@ -174,3 +174,28 @@ def test_idempotent_and_permutation_invariant(eng):
     pb = ev.EvidenceBatch(b.sites[perm], b.frags, b.splits, b.libs)
     r3 = gpu_rows(eng, pb, 2)
     assert r3.tobytes() == r1[perm].tobytes()
+
+
+def test_full_size_configs_against_oracle(eng, oracle):
+    """BASELINE.json configs[1] and configs[2] at their full sizes (10k DEL, 100k mixed) against the oracle
+    (all host threads), default kernel: these sizes run the ramped AND the 8-site work units."""
+    for config, n in (("del10k", 10_000), ("mixed100k", 100_000)):
+        b = synth.generate_parallel(config, n_sites=n)
+        got = gpu_rows(eng, b, 5)
+        exp = oracle.score(b, n_threads=oracle.max_threads())
+        assert_rows_match(got, exp, exact_gl=True, where="full-size " + config)
+        assert gpu_rows(eng, b, 6).tobytes() == got.tobytes()          # 8-site units only: same bytes
+
+
+def test_million_site_shape_properties(eng, oracle):
+    """The benchmark shape (configs[3]) at 400k sites -- above any small-batch path: the unit mapping must not
+    change a byte (variants 5 / 6 / 7), rescoring is idempotent, and a 16k-site slice equals the oracle."""
+    b = synth.generate_parallel("del1m4lib", n_sites=400_000)
+    r5 = gpu_rows(eng, b, 5)
+    assert gpu_rows(eng, b, 5).tobytes() == r5.tobytes()
+    assert gpu_rows(eng, b, 6).tobytes() == r5.tobytes()
+    assert gpu_rows(eng, b, 7).tobytes() == r5.tobytes()
+    assert gpu_rows(eng, b, 2).tobytes() == r5.tobytes()               # the previous default kernel
+    lo, hi = 123_000, 139_000
+    part = b.slice_sites(lo, hi)
+    assert_rows_match(r5[lo:hi], oracle.score(part, n_threads=oracle.max_threads()), exact_gl=True, where="1M-shape slice")
