@@ -34,6 +34,9 @@ constexpr int kD = SVGT_LEAN_DEPTH;
 #define SVGT_LEAN_FUSE_CALL 0       /* 1: the genotype call runs at the end of each work unit (one launch): measured +26 % kernel time at 1M
                                        sites (log_choose is a latency-bound loop; in svgt_call_kernel a million threads hide it), -16 % at 10k */
 #endif
+#ifndef SVGT_LEAN_BIG_RAMP
+#define SVGT_LEAN_BIG_RAMP 0        /* unit ramp for batches above ~600k sites: 0 none, 1 full, 2 single-site head only */
+#endif
 #ifndef SVGT_LEAN_CP
 #define SVGT_LEAN_CP "cp.async.cg.shared.global"        /* A/B: .ca (through L1), .L2::128B / .L2::256B prefetch hints */
 #endif
@@ -69,12 +72,14 @@ struct alignas(128) LeanSmem {
  */
 struct UnitRange { long long base; int count; };
 
+/* ramp: 0 none, 1 full (1-2-4-8), 2 short (W single-site units, then 8): large batches */
 template <int G>
-__host__ __device__ __forceinline__ UnitRange lean_unit_range(long long unit, long long W, bool ramp)
+__host__ __device__ __forceinline__ UnitRange lean_unit_range(long long unit, long long W, int ramp)
 {
     UnitRange r;
     if (!ramp || G < 8) { r.base = unit * G; r.count = G; return r; }
     if (unit < W) { r.base = unit; r.count = 1; }
+    else if (ramp == 2) { r.base = W + (unit - W) * 8; r.count = 8; }
     else if (unit < 2 * W) { r.base = W + (unit - W) * 2; r.count = 2; }
     else if (unit < 3 * W) { r.base = 3 * W + (unit - 2 * W) * 4; r.count = 4; }
     else { r.base = 7 * W + (unit - 3 * W) * 8; r.count = 8; }
@@ -82,10 +87,11 @@ __host__ __device__ __forceinline__ UnitRange lean_unit_range(long long unit, lo
 }
 
 template <int G>
-__host__ __device__ __forceinline__ long long lean_n_units(long long n_sites, long long W, bool ramp)
+__host__ __device__ __forceinline__ long long lean_n_units(long long n_sites, long long W, int ramp)
 {
     if (!ramp || G < 8) return (n_sites + G - 1) / G;
     if (n_sites <= W) return n_sites;
+    if (ramp == 2) return W + (n_sites - W + 7) / 8;
     if (n_sites <= 3 * W) return W + (n_sites - W + 1) / 2;
     if (n_sites <= 7 * W) return 2 * W + (n_sites - 3 * W + 3) / 4;
     return 3 * W + (n_sites - 7 * W + 7) / 8;
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
 
     /* phase-B role of this lane: chain c of interleaved site gb */
     const int gb = lane >> 2, c = lane & 3;
-    const bool ramp = p.n_tiles != 0;                       /* SvgtParams::n_tiles doubles as the ramp switch here */
+    const int ramp = p.n_tiles;                             /* SvgtParams::n_tiles doubles as the ramp mode here */
     const long long W = (long long)gridDim.x * kLeanWarps;
     const long long n_units = lean_n_units<G>(p.n_sites, W, ramp);
 
@@ -497,7 +503,7 @@ size_t lean_smem_bytes(const SvgtParams &p)
 struct LeanLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
 
 template <int G>
-int launch_lean(const SvgtParams &p, bool ramp, cudaStream_t stream)
+int launch_lean(const SvgtParams &p, int ramp, cudaStream_t stream)
 {
     static LeanLaunchInfo info[2] = {};
     const int a = p.assoc_mode == SVGT_ASSOC_CLASSIC ? 1 : 0;
@@ -527,9 +533,9 @@ int launch_lean(const SvgtParams &p, bool ramp, cudaStream_t stream)
     /* the ramp trades a little replay efficiency on the heaviest ~7 W sites for a short critical path:
      * worth it until the batch is large enough to amortise its longest unit (measured: +2 % kernel time
      * at 1M sites, -30 % at 200k heavy-tailed sites) */
-    if (p.n_sites >= 256 * cap * kLeanWarps) ramp = false;      /* ~600k sites on a B200 */
+    if (ramp == 1 && p.n_sites >= 256 * cap * kLeanWarps) ramp = SVGT_LEAN_BIG_RAMP;    /* ~600k sites on a B200 */
     SvgtParams q = p;
-    q.n_tiles = ramp ? 1 : 0;
+    q.n_tiles = ramp;
     kern<<<grid, SVGT_LEAN_THREADS, smem, stream>>>(q);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 #if SVGT_LEAN_FUSE_CALL
@@ -548,6 +554,6 @@ int svgt_lean_launches(void) { return SVGT_LEAN_FUSE_CALL ? 1 : 2; }
 #endif
 int svgt_launch_lean(const SvgtParams &p, int variant, cudaStream_t stream)
 {
-    if (variant == SVGT_VAR_LEAN2) return launch_lean<2>(p, false, stream);
-    return launch_lean<SVGT_LEAN_G>(p, variant != SVGT_VAR_LEAN8, stream);
+    if (variant == SVGT_VAR_LEAN2) return launch_lean<2>(p, 0, stream);
+    return launch_lean<SVGT_LEAN_G>(p, variant != SVGT_VAR_LEAN8 ? 1 : 0, stream);
 }
