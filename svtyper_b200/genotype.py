@@ -80,6 +80,59 @@ def apply_row(rec, sample_name, row, classic):
     rec.qual += sq
 
 
+class RowFormatter(object):
+    """Fast text path for the single-sample entry point: the sample column of every
+    scored row straight from the output arrays, bypassing the per-field SampleCall machinery.  Same text as
+    apply_row(..., classic=False) + VcfRecord.render(); records it cannot take (other samples in the
+    header, FORMAT values already present) go through the generic path."""
+
+    def __init__(self, header, sample_name, rows):
+        self.ok = header.samples == [sample_name]
+        self.sample = sample_name
+        keys = set(["GT", "GQ", "SQ", "GL", "AB"] + list(COUNT_FIELDS))
+        self.order = [k for k in header.format_ids() if k in keys]
+        if len(self.order) != len(keys):
+            self.ok = False
+        self.fmt = ":".join(self.order)
+        if not self.ok:
+            return
+        self.gt = rows["GT"].tolist()
+        self.gq = rows["GQ"].tolist()
+        self.sq = rows["SQ"].tolist()
+        self.gl = rows["GL"].tolist()
+        self.counts = {k: rows[k].tolist() for k in COUNT_FIELDS}
+        blank = dict(_BLANK_ITEMS)
+        self.blank_call = ":".join(str(blank[k]) for k in self.order)
+
+    def eligible(self, rec):
+        call = rec.calls.get(self.sample)
+        return (self.ok and rec.active_formats == ["GT"] and call is not None and len(call.values) == 1
+                and len(rec.calls) == 1)
+
+    def columns(self, rec, idx):
+        """(QUAL after the call, FORMAT column, sample column) of scored row `idx` for record `rec`."""
+        gt = self.gt[idx]
+        if gt == GT_BLANK or gt == GT_SKIPPED:
+            return rec.qual, self.fmt, self.blank_call
+        vals = {k: v[idx] for k, v in self.counts.items()}
+        total = vals["QR"] + vals["QA"]
+        vals["AB"] = ("%.2g" % (vals["QA"] / float(total))) if total else "."
+        vals["GL"] = ",".join("%.0f" % x for x in self.gl[idx])
+        qual = rec.qual
+        if gt == GT_UNDERFLOW:
+            vals["GQ"] = "."; vals["SQ"] = "."; vals["GT"] = "./."
+        else:
+            sq = self.sq[idx]
+            vals["GQ"] = self.gq[idx]; vals["SQ"] = "%0.2f" % sq; vals["GT"] = GT_TEXT[gt]
+            qual = qual + sq
+        return qual, self.fmt, ":".join(str(vals[k]) for k in self.order)
+
+    @staticmethod
+    def line(rec, qual, fmt, call):
+        return "\t".join((rec.chrom, str(rec.pos), rec.var_id, rec.ref, rec.alt, "%0.2f" % qual, rec.filter,
+                          rec.info_string(), fmt, call))
+
+
 class SitePlan(object):
     """Output order of a VCF: pass-through records and genotyped sites (one or two records)."""
 

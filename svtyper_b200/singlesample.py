@@ -92,11 +92,21 @@ def sso_genotype(bam_string,
                           split_weight=split_weight, disc_weight=disc_weight, assoc_mode=ev.ASSOC_SSO)
 
     vcf_out.write(header.render() + "\n")
+    fast = genotype.RowFormatter(header, sample.name, rows)
+    out = []
     for kind, rec, mate, idx in plan.entries:
+        if kind == "site" and fast.eligible(rec) and (mate is None or fast.eligible(mate)):
+            qual, fmt, call = fast.columns(rec, idx)
+            out.append(fast.line(rec, qual, fmt, call))
+            if mate is not None:                    # BND mates share one genotype (singlesample.py:648-652)
+                out.append(fast.line(mate, qual, fmt, call))
+            continue
         if kind == "site":
             genotype.apply_row(rec, sample.name, rows[idx], classic=False)
-        vcf_out.write(rec.render() + "\n")
+        out.append(rec.render())
         if mate is not None:
             mate.adopt_calls(rec)
-            vcf_out.write(mate.render() + "\n")
+            out.append(mate.render())
+    if out:
+        vcf_out.write("\n".join(out) + "\n")
     sample.close()
