@@ -3,18 +3,26 @@
  * (phase A one evidence row per lane, phase B one ordered fp64 chain per lane; reference
  * singlesample.py:355-404) with the lean row scorer of svgt_lean.cuh.
  *
- * What differs from svgt_tally_kernel (svgt_coop.cu), all of it aimed at the two limits ncu showed
- * there -- instruction issue and shared-memory wavefronts, not HBM:
- *   - per site the kernel pre-digests SiteF (two uniform LDS.128 per chunk) and per (site, library)
- *     WinF (two LDS.128 per row instead of four); non-fast sites (inversions, breakends on two
- *     contigs, a breakend within min_aligned of the contig start) build the cooperative kernel's
- *     windows on demand and take its scorer, so every batch is still covered;
+ * What differs from svgt_tally_kernel (svgt_coop.cu), all of it aimed at the limits ncu showed there --
+ * instruction issue and shared-memory wavefronts, not HBM:
+ *   - rows travel HBM -> shared memory through a per-warp cp.async ring (each lane copies and later reads
+ *     its own row: no registers or scoreboards held by rows in flight), one chunk stream per unit:
+ *     fragment chunks step-major over the live sites, then split chunks;
+ *   - per site the kernel pre-digests SiteF (two uniform LDS.128 per chunk; three for the general chain),
+ *     SplitF, the row streams, and per (site, library) WinF (two LDS.128 per row instead of four).  Sites
+ *     with both is_ref_seq windows valid take fast_row (one contig, not an inversion) or fast_row_gen
+ *     (two contigs and / or inversion); a breakend within min_aligned of the contig start builds the
+ *     cooperative kernel's windows on demand and takes its scorer, so every batch is still covered;
  *   - the insert-size histograms of the first four libraries live in shared memory with a zero
- *     sentinel behind each, so a look-up is an index clamp; the literal fp64 path reads the
- *     global copy;
- *   - a row parks 24 bytes {a + b, p_ref, p_alt} (plus the two LUT indices only when phase B can
- *     need them), as one STS.64 and one STS.128.
- * The genotype call is the same second launch (svgt_call_kernel, svgt_coop.cu).
+ *     sentinel behind each, so a look-up is an index clamp; the literal fp64 path reads the global copy;
+ *   - a row parks 24 bytes {a + b, p_ref, p_alt} structure-of-arrays (three conflict-free STS.64); the
+ *     two LUT indices replace a + b only where phase B needs a and b separately;
+ *   - one CTA of 16 warps per SM (the per-CTA tables are paid once), work units claimed one ahead, a
+ *     1-2-4-8 ramp of unit sizes for batches too small to amortise an 8-site unit of the heaviest sites.
+ * The genotype call is the same second launch (svgt_call_kernel, svgt_coop.cu); running it inside this
+ * kernel is a build switch that measured slower (SVGT_LEAN_FUSE_CALL).  Other measured switches:
+ * SVGT_LEAN_TMA (cp.async.bulk per chunk), SVGT_LEAN_DEPTH, SVGT_LEAN_CP, SVGT_LEAN_BIG_RAMP
+ * (profiles/README.md has the numbers).
  */
 #include "svgt_lean.cuh"
 
@@ -466,12 +474,9 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 }
             }
         }
-        __syncwarp();
-        if (false) {
 #else
         /* ---- park the five sums in the site's output row (lane 4g+c holds chain c of site g) ---- */
         if (gb < G && c < 3) {
-#endif
             const int site = ws.site[gb].slot;
             if (site >= 0 && (ws.site[gb].nf | ws.site[gb].ns)) {
                 double *row = reinterpret_cast<double *>(p.out + site);
@@ -481,6 +486,7 @@ __global__ void __launch_bounds__(SVGT_LEAN_THREADS, SVGT_LEAN_MINB) svgt_lean_k
                 else row[4] = sum_frag;
             }
         }
+#endif
         __syncwarp();
     }
     if (err) {
