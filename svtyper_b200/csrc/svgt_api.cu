@@ -127,10 +127,14 @@ int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, voi
 /* ------------------------------------------------------------------------------------ */
 /* host-buffer context                                                                   */
 /* ------------------------------------------------------------------------------------ */
+enum { kSlices = 8 };            /* pipelined host path: site slices in flight */
+
 struct svgt_ctx {
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream;         /* compute (and everything, in the one-shot path) */
+    cudaStream_t s_h2d, s_d2h;   /* pipelined path: copy streams either side of the kernels */
     cudaEvent_t ev0, ev1;
+    cudaEvent_t up[kSlices], k0[kSlices], k1[kSlices];
     void *buf[12];
     size_t cap[12];
     int64_t h2d, d2h;
@@ -178,6 +182,13 @@ int svgt_ctx_create(int device, svgt_ctx_t **out)
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { free(c); return cuda_fail(e, "cudaStreamCreate"); }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < kSlices; ++i) {
+        cudaEventCreateWithFlags(&c->up[i], cudaEventDisableTiming);
+        cudaEventCreate(&c->k0[i]);
+        cudaEventCreate(&c->k1[i]);
+    }
     *out = c;
     return SVGT_OK;
 }
@@ -190,9 +201,128 @@ int svgt_ctx_destroy(svgt_ctx_t *c)
         if (c->buf[i]) cudaFree(c->buf[i]);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (int i = 0; i < kSlices; ++i) { cudaEventDestroy(c->up[i]); cudaEventDestroy(c->k0[i]); cudaEventDestroy(c->k1[i]); }
+    cudaStreamDestroy(c->s_h2d);
+    cudaStreamDestroy(c->s_d2h);
     cudaStreamDestroy(c->stream);
     free(c);
     return SVGT_OK;
+}
+
+/*
+ * Pipelined host path for large batches: the sites are cut into kSlices contiguous slices; slice k's rows
+ * go up on the H2D stream while slice k-1 is scored and slice k-2's result rows come back on the D2H
+ * stream.  It relies on the rows being laid out in site order (every packer in this repo does that): a
+ * slice is launched with n_frag / n_split = the prefix uploaded so far, so a site whose rows lie beyond it
+ * trips the kernel's own bounds check (SVGT_ERR_ARG) and the caller falls back to the one-shot path.
+ * Slices are scored in identity order (the launch permutation spans the whole batch); the imbalance hides
+ * under the copies.  Returns 1 when it handled the batch, 0 to fall back, negative on a real error.
+ */
+static int64_t site_off(const int32_t *row, int lo) { return (int64_t)(uint32_t)row[lo] | ((int64_t)row[lo + 1] << 32); }
+
+static int ctx_score_pipelined(svgt_ctx *c, const svgt_batch_t *hb, void *out_rows_host)
+{
+    const int64_t n = hb->n_sites;
+    int rc;
+    svgt_batch_t db = *hb;
+    cudaError_t e;
+#define UPS(slot, field, type, count)                                                         \
+    do {                                                                                      \
+        const size_t bytes_ = (size_t)(count) * sizeof(type);                                 \
+        if ((rc = ctx_reserve(c, slot, bytes_)) != SVGT_OK) return rc;                        \
+        if (bytes_) {                                                                         \
+            e = cudaMemcpyAsync(c->buf[slot], hb->field, bytes_, cudaMemcpyHostToDevice, c->s_h2d); \
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");                \
+            c->h2d += (int64_t)bytes_;                                                        \
+        }                                                                                     \
+        db.field = (const type *)c->buf[slot];                                                \
+    } while (0)
+    UPS(B_LIBF, lib_f64, double, hb->n_lib * 4);
+    UPS(B_LIBI, lib_i32, int32_t, hb->n_lib * 4);
+    UPS(B_HIST, hist, uint32_t, hb->n_hist);
+    UPS(B_PM, pm, double, 256);
+    UPS(B_LOG, logt, double, hb->n_log);
+    UPS(B_CONSTS, consts, double, 32);
+#undef UPS
+    if ((rc = ctx_reserve(c, B_SITES, (size_t)n * SVGT_SITE_WORDS * 4)) != SVGT_OK) return rc;
+    if ((rc = ctx_reserve(c, B_FRAGS, (size_t)hb->n_frag * SVGT_FRAG_WORDS * 4)) != SVGT_OK) return rc;
+    if ((rc = ctx_reserve(c, B_SPLITS, (size_t)hb->n_split * SVGT_SPLIT_WORDS * 4)) != SVGT_OK) return rc;
+    if ((rc = ctx_reserve(c, B_OUT, (size_t)n * SVGT_OUT_BYTES)) != SVGT_OK) return rc;
+    if ((rc = ctx_reserve(c, B_STATUS, 16 * kSlices)) != SVGT_OK) return rc;
+    db.sites = nullptr; db.order = nullptr;
+    db.frags = (const int32_t *)c->buf[B_FRAGS];
+    db.splits = (const int32_t *)c->buf[B_SPLITS];
+
+    int64_t prev_f = 0, prev_s = 0;
+    for (int k = 0; k < kSlices; ++k) {
+        const int64_t s0 = n * k / kSlices, s1 = n * (k + 1) / kSlices;
+        int64_t end_f = hb->n_frag, end_s = hb->n_split;
+        if (s1 < n) {                                   /* the next slice's first rows end this slice's prefix */
+            const int32_t *row = hb->sites + s1 * SVGT_SITE_WORDS;
+            end_f = site_off(row, 10); end_s = site_off(row, 13);
+        }
+        if (end_f < prev_f || end_f > hb->n_frag || end_s < prev_s || end_s > hb->n_split) {
+            cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h);
+            return 0;                                   /* not laid out in site order */
+        }
+        const size_t bs = (size_t)(s1 - s0) * SVGT_SITE_WORDS * 4, bf = (size_t)(end_f - prev_f) * SVGT_FRAG_WORDS * 4,
+                     bp = (size_t)(end_s - prev_s) * SVGT_SPLIT_WORDS * 4;
+        if (bs && (e = cudaMemcpyAsync((char *)c->buf[B_SITES] + (size_t)s0 * SVGT_SITE_WORDS * 4,
+                                       hb->sites + s0 * SVGT_SITE_WORDS, bs, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+        if (bf && (e = cudaMemcpyAsync((char *)c->buf[B_FRAGS] + (size_t)prev_f * SVGT_FRAG_WORDS * 4,
+                                       hb->frags + prev_f * SVGT_FRAG_WORDS, bf, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+        if (bp && (e = cudaMemcpyAsync((char *)c->buf[B_SPLITS] + (size_t)prev_s * SVGT_SPLIT_WORDS * 4,
+                                       hb->splits + prev_s * SVGT_SPLIT_WORDS, bp, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+        c->h2d += (int64_t)(bs + bf + bp);
+        prev_f = end_f; prev_s = end_s;
+        cudaEventRecord(c->up[k], c->s_h2d);
+        if (s1 == s0) continue;
+        cudaStreamWaitEvent(c->stream, c->up[k], 0);
+        svgt_batch_t sb = db;
+        sb.sites = (const int32_t *)c->buf[B_SITES] + s0 * SVGT_SITE_WORDS;
+        sb.n_sites = s1 - s0; sb.n_frag = end_f; sb.n_split = end_s;
+        cudaEventRecord(c->k0[k], c->stream);
+        rc = svgt_score_batch(&sb, (char *)c->buf[B_OUT] + (size_t)s0 * SVGT_OUT_BYTES, (int32_t *)c->buf[B_STATUS] + 4 * k,
+                              c->stream);
+        if (rc != SVGT_OK) return rc;
+        cudaEventRecord(c->k1[k], c->stream);
+        cudaStreamWaitEvent(c->s_d2h, c->k1[k], 0);
+        e = cudaMemcpyAsync((char *)out_rows_host + (size_t)s0 * SVGT_OUT_BYTES, (char *)c->buf[B_OUT] + (size_t)s0 * SVGT_OUT_BYTES,
+                            (size_t)(s1 - s0) * SVGT_OUT_BYTES, cudaMemcpyDeviceToHost, c->s_d2h);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H)");
+        c->d2h += (s1 - s0) * (int64_t)SVGT_OUT_BYTES;
+    }
+    int32_t status[4 * kSlices];
+    memset(status, 0, sizeof(status));
+    cudaStreamWaitEvent(c->s_d2h, c->k1[kSlices - 1], 0);
+    e = cudaMemcpyAsync(status, c->buf[B_STATUS], sizeof(status), cudaMemcpyDeviceToHost, c->s_d2h);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(status)");
+    c->d2h += (int64_t)sizeof(status);
+    if ((e = cudaStreamSynchronize(c->s_d2h)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    c->kernel_ms = 0.f;
+    for (int k = 0; k < kSlices; ++k) {
+        if (n * (k + 1) / kSlices == n * k / kSlices) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->k0[k], c->k1[k]);
+        c->kernel_ms += ms;
+    }
+    int first = 0, count = 0;
+    for (int k = 0; k < kSlices; ++k) {
+        if (n * (k + 1) / kSlices == n * k / kSlices) continue;
+        if (status[4 * k] != 0 && first == 0) first = status[4 * k];
+        count += status[4 * k + 2];
+    }
+    if (first == SVGT_ERR_ARG) return 0;                /* possibly rows outside a slice's prefix: redo in one shot */
+    if (first != 0) {
+        char msg[64];
+        snprintf(msg, sizeof(msg), "%d site(s), first code %d", count, first);
+        return fail(first, "scoring kernel flagged %s", msg);
+    }
+    return 1;
 }
 
 int svgt_ctx_score_host(svgt_ctx_t *c, const svgt_batch_t *hb, void *out_rows_host)
@@ -205,6 +335,19 @@ int svgt_ctx_score_host(svgt_ctx_t *c, const svgt_batch_t *hb, void *out_rows_ho
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     c->h2d = c->d2h = 0;
     c->kernel_ms = 0.f;
+
+    /* large batches: overlap the copies with the kernels (SVGT_PIPELINE_MIN_SITES overrides the threshold,
+     * 0 disables) */
+    static const long long min_sites = [] {
+        const char *v = getenv("SVGT_PIPELINE_MIN_SITES");
+        return v && *v ? atoll(v) : 131072LL;
+    }();
+    if (min_sites > 0 && hb->n_sites >= min_sites) {
+        rc = ctx_score_pipelined(c, hb, out_rows_host);
+        if (rc != 0) return rc < 0 ? rc : SVGT_OK;
+        c->h2d = c->d2h = 0;
+        c->kernel_ms = 0.f;
+    }
 
     svgt_batch_t db = *hb;
 #define UP(slot, field, type, count)                                                          \

@@ -3,6 +3,8 @@
 Integer FORMAT fields and GT bit-exact; GL bit-exact against the oracle (same LUTs, same
 IEEE operation order) and within 1e-6 of the reference's golden values; SQ within 1e-9.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -199,3 +201,37 @@ def test_million_site_shape_properties(eng, oracle):
     lo, hi = 123_000, 139_000
     part = b.slice_sites(lo, hi)
     assert_rows_match(r5[lo:hi], oracle.score(part, n_threads=oracle.max_threads()), exact_gl=True, where="1M-shape slice")
+
+
+def test_pipelined_host_path(tmp_path):
+    """svgt_ctx_score_host overlaps H2D / kernels / D2H over site slices for large batches.  Forced on for a
+    small batch in a child process (the threshold is read once per process): same bytes as the device path
+    and the oracle; a batch whose rows are NOT laid out in site order must fall back and still be right."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from svtyper_b200 import engine, evidence as ev, native, synth
+from oracle import oracle
+eng = engine.Engine(0)
+b = synth.generate("mixed100k", n_sites=6000, seed=31)
+want = oracle.score(b)
+dev = eng.upload(b); eng.score(dev); ref = eng.rows(dev)
+got = eng.score_host(b)
+assert got.tobytes() == ref.tobytes()
+for k in ("GT", "GQ", "DP", "RO", "AO", "QR", "QA", "RS", "AS", "ASC", "RP", "AP"):
+    assert np.array_equal(got[k], want[k]), k
+assert eng.last_h2d >= b.sites.nbytes + b.frags.nbytes + b.splits.nbytes
+perm = np.random.default_rng(3).permutation(b.n_sites)
+pb = ev.EvidenceBatch(b.sites[perm], b.frags, b.splits, b.libs)        # offsets no longer monotonic
+got2 = eng.score_host(pb)
+assert got2.tobytes() == ref[perm].tobytes()
+e = ev.EvidenceBatch(b.sites[:5], b.frags, b.splits, b.libs)           # fewer sites than slices
+assert eng.score_host(e).tobytes() == ref[:5].tobytes()
+print("pipelined ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    env = dict(os.environ, SVGT_PIPELINE_MIN_SITES="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "pipelined ok" in r.stdout, r.stderr[-1500:]
