@@ -178,3 +178,35 @@ def test_bad_alignment_name_exits():
     with pytest.raises(SystemExit):
         classic.sv_genotype("reads.sam", io.StringIO(""), io.StringIO(), 20, 1, 1, 1000, None, False, None, None,
                             False, None, 1e10)
+
+
+@needs_ref
+def test_sso_records_with_existing_format_values_match_reference(ref, oracle_scorer, tmp_path):
+    """Records that already carry FORMAT values for the sample (and a FORMAT key svtyper does not write)
+    cannot take the direct text path (genotype.RowFormatter): the generic record model must give the
+    reference's text for them, next to fast-path records in the same file."""
+    lines = open(VCF).read().split("\n")
+    head = [l for l in lines if l.startswith("##")]
+    head.append('##FORMAT=<ID=XX,Number=1,Type=Integer,Description="pre-existing per-sample value">')
+    chrom_line = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tNA12878"
+    body = [l for l in lines if l and not l.startswith("#")][:40]
+    out = []
+    for i, l in enumerate(body):
+        c = l.split("\t")[:8]
+        if i % 3 == 0:
+            c += ["GT:XX", "0/1:%d" % (i + 1)]
+        elif i % 3 == 1:
+            c += ["GT", "./."]
+        out.append("\t".join(c))
+    path = tmp_path / "fmt.vcf"
+    path.write_text("\n".join(head + [chrom_line] + out) + "\n")
+    args = (20, 1, 1, 1000000, LIB, False, None, False, 1000, 1e10, None, 1000)
+    theirs = tmp_path / "ref.vcf"
+    with open(path) as fin, open(theirs, "w") as fout:
+        ref.singlesample.sso_genotype(BAM, fin, fout, *args)
+    mine = tmp_path / "mine.vcf"
+    with open(path) as fin, open(mine, "w") as fout:
+        singlesample.sso_genotype(BAM, fin, fout, *args)
+    got, want = _strip(open(mine).read()), _strip(open(theirs).read())
+    assert got == want
+    assert any(":XX" in l.split("\t")[8] for l in got if not l.startswith("#") and l)
