@@ -134,7 +134,8 @@ class NativeBam(object):
     def pack(self, sites, rg_names, rg_lib, lib_active, mode, max_reads, threads=0):
         """sites: [(tidA, begA, endA, tidB, begB, endB)] -> (counts[n,4] int32, frags[n,8], splits[n,8])."""
         n = len(sites)
-        arr = (Site * max(n, 1))(*[Site(*s) for s in sites])
+        flat = np.ascontiguousarray(np.asarray(sites, dtype=np.int32).reshape(-1, 6)) if n else np.zeros((1, 6), np.int32)
+        arr = ctypes.cast(flat.ctypes.data, ctypes.POINTER(Site))
         counts = (Count * max(n, 1))()
         names = (ctypes.c_char_p * max(len(rg_names), 1))(*[r.encode("ascii") for r in rg_names])
         libs = (ctypes.c_int32 * max(len(rg_lib), 1))(*rg_lib)
@@ -200,11 +201,12 @@ def scan_libraries(bam, readgroups_per_lib, num_samp, read_length_reads=10000, p
         nb.close()
 
 
-def fetch_windows(sample, breakpoint, z, mode):
+def fetch_windows(sample, breakpoint, z, mode, flank=None):
     """The two fetch windows as the integers the BAM layer sees (reference classic.py:62-78,
     singlesample.py:139-157): the flank arithmetic is fp64, the reader truncates."""
     bam = sample.bam
-    flank = sample.fetch_flank(z)
+    if flank is None:
+        flank = sample.fetch_flank(z)
     out = []
     for side in ("A", "B"):
         end = breakpoint[side]
@@ -223,7 +225,8 @@ def pack_sample(sample, plan, mode, max_reads, z=3, threads=0):
     path = sample.bam.filename.decode() if isinstance(sample.bam.filename, bytes) else str(sample.bam.filename)
     nb = NativeBam(path)
     try:
-        sites = [fetch_windows(sample, bp, z, mode) for bp in plan.breakpoints]
+        flank = sample.fetch_flank(z)                       # one value per sample: max(mean + z * sd) over its libraries
+        sites = [fetch_windows(sample, bp, z, mode, flank) for bp in plan.breakpoints]
         rg_names = list(sample.rg_to_lib.keys())
         rg_lib = [sample.rg_to_lib[r] for r in rg_names]
         n_lib = len(sample.libraries)
