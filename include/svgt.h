@@ -27,11 +27,13 @@
 extern "C" {
 #endif
 
-#define SVGT_ABI_VERSION 1
+#define SVGT_ABI_VERSION 2
 
 #define SVGT_SITE_WORDS 16  /* int32 words per site row      (64 B) */
 #define SVGT_FRAG_WORDS 8   /* int32 words per fragment row  (32 B) */
 #define SVGT_SPLIT_WORDS 8  /* int32 words per split row     (32 B) */
+#define SVGT_CSITE_WORDS 12 /* compact schema: int32 words per site row (48 B)  */
+#define SVGT_CROW_WORDS 4   /* compact schema: int32 words per evidence row (16 B) */
 #define SVGT_OUT_BYTES 80   /* f64 GL[3], f64 SQ, int32 GT,GQ,DP,RO,AO,QR,QA,RS,AS,ASC,RP,AP */
 
 enum svgt_err {
@@ -83,6 +85,39 @@ typedef struct svgt_batch {
     double split_weight, disc_weight;         /* reference --split_weight/--disc_weight  */
 } svgt_batch_t;
 
+/*
+ * The same batch in the COMPACT schema (svtyper_b200/compact.py; the default product path): 48-byte site
+ * rows, and one array of 16-byte rows holding each site's fragment rows followed by its split rows.
+ * In svgt_score_compact() every pointer is a DEVICE pointer; in svgt_ctx_score_host_compact() every
+ * pointer is a HOST pointer (out_final / done_flag must be NULL there).
+ */
+#define SVGT_LAYOUT_SITE_ORDER 1   /* flags: rows are laid out in site order (row_off non-decreasing, each
+                                      site's rows directly behind the previous site's) -- what every packer
+                                      of this repo emits; lets the host path pipeline site slices         */
+typedef struct svgt_cbatch {
+    const int32_t *sites;   int64_t n_sites;  /* [n_sites][12]                           */
+    const int32_t *rows;    int64_t n_rows;   /* [n_rows][4]                             */
+    const int32_t *order;                     /* optional launch permutation, NULL = identity */
+    const double *lib_f64;                    /* [n_lib][4] flank, 2*sd, N, mean         */
+    const int32_t *lib_i32;                   /* [n_lib][4] hist_off, hist_len, nondel_L */
+    int32_t n_lib;
+    uint32_t hist_max;                        /* largest histogram count; 0 = unknown    */
+    const uint32_t *hist;   int64_t n_hist;
+    const double *pm;                         /* [256]                                   */
+    const double *logt;     int64_t n_log;
+    const double *consts;                     /* [32]                                    */
+    int32_t min_aligned, split_slop, assoc_mode;
+    int32_t unit_mode;                        /* 0 default; 1 / 2: fixed 8- / 2-site work units (tests) */
+    double split_weight, disc_weight;
+    void *out_final;                          /* optional: the final 80-byte rows go HERE instead of out_rows
+                                                 (e.g. a peer-mapped buffer of the gathering GPU); out_rows
+                                                 is then scratch                                          */
+    int32_t *done_flag;                       /* optional: set to done_value with system scope after the
+                                                 last final row is written (may be peer-mapped)           */
+    int32_t done_value;
+    int32_t flags;                            /* SVGT_LAYOUT_*                           */
+} svgt_cbatch_t;
+
 int svgt_abi_version(void);
 const char *svgt_last_error(void);            /* thread-local, valid until the next call */
 int svgt_device_count(void);
@@ -94,6 +129,9 @@ int svgt_device_count(void);
  * 0 or the first svgt_err a site raised.  The callee allocates nothing.
  */
 int svgt_score_batch(const svgt_batch_t *batch, void *out_rows, int32_t *status, void *stream);
+
+/* The same for a compact batch: the default path (svgt_compact_kernel + svgt_call_compact_kernel). */
+int svgt_score_compact(const svgt_cbatch_t *batch, void *out_rows, int32_t *status, void *stream);
 
 /* Number of kernel launches svgt_score_batch issues for this batch (bench bookkeeping). */
 int svgt_launches_per_batch(const svgt_batch_t *batch);
@@ -120,10 +158,24 @@ typedef struct svgt_ctx svgt_ctx_t;
 int svgt_ctx_create(int device, svgt_ctx_t **ctx);
 int svgt_ctx_destroy(svgt_ctx_t *ctx);
 int svgt_ctx_score_host(svgt_ctx_t *ctx, const svgt_batch_t *host_batch, void *out_rows_host);
+int svgt_ctx_score_host_compact(svgt_ctx_t *ctx, const svgt_cbatch_t *host_batch, void *out_rows_host);
 /* bytes moved by the last svgt_ctx_score_host call */
 int svgt_ctx_last_traffic(const svgt_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* device time (ms, CUDA events) of the kernel(s) in the last svgt_ctx_score_host call */
 int svgt_ctx_last_kernel_ms(const svgt_ctx_t *ctx, float *ms);
+
+/*
+ * Multi-GPU output without a collective: a buffer of the gathering rank that the other ranks' call
+ * kernels write straight into over NVLink.  svgt_shared_alloc() cudaMalloc's `bytes` on the current
+ * device and exports a 64-byte CUDA IPC handle; svgt_shared_open() maps such a handle in another
+ * process (peer access is enabled by the mapping); svgt_wait_flags() enqueues, on `stream`, a wait until
+ * flags[i] >= value for all i < n (flags: device memory of the current device).
+ */
+int svgt_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[64]);
+int svgt_shared_open(const unsigned char handle[64], void **dev_ptr);
+int svgt_shared_close(void *dev_ptr);
+int svgt_shared_free(void *dev_ptr);
+int svgt_wait_flags(const int32_t *flags, int32_t n, int32_t value, void *stream);
 
 #ifdef __cplusplus
 }

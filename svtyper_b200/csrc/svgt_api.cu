@@ -62,7 +62,25 @@ int check_batch(const svgt_batch_t *b)
 
 }  // namespace
 
+__global__ void svgt_wait_flags_kernel(const volatile int *flags, int n, int value)
+{
+    const int i = threadIdx.x;
+    if (i < n) {
+        while (flags[i] < value) __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 extern "C" {
+
+int svgt_wait_flags(const int32_t *flags, int32_t n, int32_t value, void *stream)
+{
+    if (!flags || n < 0 || n > 1024) return fail(SVGT_ERR_ARG, "bad %s", "svgt_wait_flags arguments");
+    if (n == 0) return SVGT_OK;
+    svgt_wait_flags_kernel<<<1, ((n + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(flags, n, value);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "svgt_wait_flags launch");
+}
 
 int svgt_abi_version(void) { return SVGT_ABI_VERSION; }
 
@@ -209,122 +227,6 @@ int svgt_ctx_destroy(svgt_ctx_t *c)
     return SVGT_OK;
 }
 
-/*
- * Pipelined host path for large batches: the sites are cut into kSlices contiguous slices; slice k's rows
- * go up on the H2D stream while slice k-1 is scored and slice k-2's result rows come back on the D2H
- * stream.  It relies on the rows being laid out in site order (every packer in this repo does that): a
- * slice is launched with n_frag / n_split = the prefix uploaded so far, so a site whose rows lie beyond it
- * trips the kernel's own bounds check (SVGT_ERR_ARG) and the caller falls back to the one-shot path.
- * Slices are scored in identity order (the launch permutation spans the whole batch); the imbalance hides
- * under the copies.  Returns 1 when it handled the batch, 0 to fall back, negative on a real error.
- */
-static int64_t site_off(const int32_t *row, int lo) { return (int64_t)(uint32_t)row[lo] | ((int64_t)row[lo + 1] << 32); }
-
-static int ctx_score_pipelined(svgt_ctx *c, const svgt_batch_t *hb, void *out_rows_host)
-{
-    const int64_t n = hb->n_sites;
-    int rc;
-    svgt_batch_t db = *hb;
-    cudaError_t e;
-#define UPS(slot, field, type, count)                                                         \
-    do {                                                                                      \
-        const size_t bytes_ = (size_t)(count) * sizeof(type);                                 \
-        if ((rc = ctx_reserve(c, slot, bytes_)) != SVGT_OK) return rc;                        \
-        if (bytes_) {                                                                         \
-            e = cudaMemcpyAsync(c->buf[slot], hb->field, bytes_, cudaMemcpyHostToDevice, c->s_h2d); \
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");                \
-            c->h2d += (int64_t)bytes_;                                                        \
-        }                                                                                     \
-        db.field = (const type *)c->buf[slot];                                                \
-    } while (0)
-    UPS(B_LIBF, lib_f64, double, hb->n_lib * 4);
-    UPS(B_LIBI, lib_i32, int32_t, hb->n_lib * 4);
-    UPS(B_HIST, hist, uint32_t, hb->n_hist);
-    UPS(B_PM, pm, double, 256);
-    UPS(B_LOG, logt, double, hb->n_log);
-    UPS(B_CONSTS, consts, double, 32);
-#undef UPS
-    if ((rc = ctx_reserve(c, B_SITES, (size_t)n * SVGT_SITE_WORDS * 4)) != SVGT_OK) return rc;
-    if ((rc = ctx_reserve(c, B_FRAGS, (size_t)hb->n_frag * SVGT_FRAG_WORDS * 4)) != SVGT_OK) return rc;
-    if ((rc = ctx_reserve(c, B_SPLITS, (size_t)hb->n_split * SVGT_SPLIT_WORDS * 4)) != SVGT_OK) return rc;
-    if ((rc = ctx_reserve(c, B_OUT, (size_t)n * SVGT_OUT_BYTES)) != SVGT_OK) return rc;
-    if ((rc = ctx_reserve(c, B_STATUS, 16 * kSlices)) != SVGT_OK) return rc;
-    db.sites = nullptr; db.order = nullptr;
-    db.frags = (const int32_t *)c->buf[B_FRAGS];
-    db.splits = (const int32_t *)c->buf[B_SPLITS];
-
-    int64_t prev_f = 0, prev_s = 0;
-    for (int k = 0; k < kSlices; ++k) {
-        const int64_t s0 = n * k / kSlices, s1 = n * (k + 1) / kSlices;
-        int64_t end_f = hb->n_frag, end_s = hb->n_split;
-        if (s1 < n) {                                   /* the next slice's first rows end this slice's prefix */
-            const int32_t *row = hb->sites + s1 * SVGT_SITE_WORDS;
-            end_f = site_off(row, 10); end_s = site_off(row, 13);
-        }
-        if (end_f < prev_f || end_f > hb->n_frag || end_s < prev_s || end_s > hb->n_split) {
-            cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h);
-            return 0;                                   /* not laid out in site order */
-        }
-        const size_t bs = (size_t)(s1 - s0) * SVGT_SITE_WORDS * 4, bf = (size_t)(end_f - prev_f) * SVGT_FRAG_WORDS * 4,
-                     bp = (size_t)(end_s - prev_s) * SVGT_SPLIT_WORDS * 4;
-        if (bs && (e = cudaMemcpyAsync((char *)c->buf[B_SITES] + (size_t)s0 * SVGT_SITE_WORDS * 4,
-                                       hb->sites + s0 * SVGT_SITE_WORDS, bs, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
-            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-        if (bf && (e = cudaMemcpyAsync((char *)c->buf[B_FRAGS] + (size_t)prev_f * SVGT_FRAG_WORDS * 4,
-                                       hb->frags + prev_f * SVGT_FRAG_WORDS, bf, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
-            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-        if (bp && (e = cudaMemcpyAsync((char *)c->buf[B_SPLITS] + (size_t)prev_s * SVGT_SPLIT_WORDS * 4,
-                                       hb->splits + prev_s * SVGT_SPLIT_WORDS, bp, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
-            return cuda_fail(e, "cudaMemcpyAsync(H2D)");
-        c->h2d += (int64_t)(bs + bf + bp);
-        prev_f = end_f; prev_s = end_s;
-        cudaEventRecord(c->up[k], c->s_h2d);
-        if (s1 == s0) continue;
-        cudaStreamWaitEvent(c->stream, c->up[k], 0);
-        svgt_batch_t sb = db;
-        sb.sites = (const int32_t *)c->buf[B_SITES] + s0 * SVGT_SITE_WORDS;
-        sb.n_sites = s1 - s0; sb.n_frag = end_f; sb.n_split = end_s;
-        cudaEventRecord(c->k0[k], c->stream);
-        rc = svgt_score_batch(&sb, (char *)c->buf[B_OUT] + (size_t)s0 * SVGT_OUT_BYTES, (int32_t *)c->buf[B_STATUS] + 4 * k,
-                              c->stream);
-        if (rc != SVGT_OK) return rc;
-        cudaEventRecord(c->k1[k], c->stream);
-        cudaStreamWaitEvent(c->s_d2h, c->k1[k], 0);
-        e = cudaMemcpyAsync((char *)out_rows_host + (size_t)s0 * SVGT_OUT_BYTES, (char *)c->buf[B_OUT] + (size_t)s0 * SVGT_OUT_BYTES,
-                            (size_t)(s1 - s0) * SVGT_OUT_BYTES, cudaMemcpyDeviceToHost, c->s_d2h);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(D2H)");
-        c->d2h += (s1 - s0) * (int64_t)SVGT_OUT_BYTES;
-    }
-    int32_t status[4 * kSlices];
-    memset(status, 0, sizeof(status));
-    cudaStreamWaitEvent(c->s_d2h, c->k1[kSlices - 1], 0);
-    e = cudaMemcpyAsync(status, c->buf[B_STATUS], sizeof(status), cudaMemcpyDeviceToHost, c->s_d2h);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(status)");
-    c->d2h += (int64_t)sizeof(status);
-    if ((e = cudaStreamSynchronize(c->s_d2h)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
-    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
-    c->kernel_ms = 0.f;
-    for (int k = 0; k < kSlices; ++k) {
-        if (n * (k + 1) / kSlices == n * k / kSlices) continue;
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, c->k0[k], c->k1[k]);
-        c->kernel_ms += ms;
-    }
-    int first = 0, count = 0;
-    for (int k = 0; k < kSlices; ++k) {
-        if (n * (k + 1) / kSlices == n * k / kSlices) continue;
-        if (status[4 * k] != 0 && first == 0) first = status[4 * k];
-        count += status[4 * k + 2];
-    }
-    if (first == SVGT_ERR_ARG) return 0;                /* possibly rows outside a slice's prefix: redo in one shot */
-    if (first != 0) {
-        char msg[64];
-        snprintf(msg, sizeof(msg), "%d site(s), first code %d", count, first);
-        return fail(first, "scoring kernel flagged %s", msg);
-    }
-    return 1;
-}
-
 int svgt_ctx_score_host(svgt_ctx_t *c, const svgt_batch_t *hb, void *out_rows_host)
 {
     if (!c) return fail(SVGT_ERR_ARG, "null %s", "ctx");
@@ -335,19 +237,6 @@ int svgt_ctx_score_host(svgt_ctx_t *c, const svgt_batch_t *hb, void *out_rows_ho
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     c->h2d = c->d2h = 0;
     c->kernel_ms = 0.f;
-
-    /* large batches: overlap the copies with the kernels (SVGT_PIPELINE_MIN_SITES overrides the threshold,
-     * 0 disables) */
-    static const long long min_sites = [] {
-        const char *v = getenv("SVGT_PIPELINE_MIN_SITES");
-        return v && *v ? atoll(v) : 131072LL;
-    }();
-    if (min_sites > 0 && hb->n_sites >= min_sites) {
-        rc = ctx_score_pipelined(c, hb, out_rows_host);
-        if (rc != 0) return rc < 0 ? rc : SVGT_OK;
-        c->h2d = c->d2h = 0;
-        c->kernel_ms = 0.f;
-    }
 
     svgt_batch_t db = *hb;
 #define UP(slot, field, type, count)                                                          \
@@ -394,6 +283,288 @@ int svgt_ctx_score_host(svgt_ctx_t *c, const svgt_batch_t *hb, void *out_rows_ho
         return fail(status[0], "scoring kernel flagged %s", msg);
     }
     return SVGT_OK;
+}
+
+
+/* ------------------------------------------------------------------------------------ */
+/* compact schema (the default path)                                                     */
+/* ------------------------------------------------------------------------------------ */
+static int check_cbatch(const svgt_cbatch_t *b)
+{
+    if (!b) return fail(SVGT_ERR_ARG, "null batch%s", nullptr);
+    if (b->n_sites < 0 || b->n_rows < 0 || b->n_lib < 0 || b->n_hist < 0 || b->n_log < 2)
+        return fail(SVGT_ERR_ARG, "negative size in batch%s", nullptr);
+    if (b->n_sites > 0 && !b->sites) return fail(SVGT_ERR_ARG, "null %s", "sites");
+    if (b->n_rows > 0 && !b->rows) return fail(SVGT_ERR_ARG, "null %s", "rows");
+    if (b->n_lib > 0 && (!b->lib_f64 || !b->lib_i32 || !b->hist)) return fail(SVGT_ERR_ARG, "null %s", "library tables");
+    if (!b->pm || !b->logt || !b->consts) return fail(SVGT_ERR_ARG, "null %s", "look-up tables");
+    if (b->assoc_mode != SVGT_ASSOC_SSO && b->assoc_mode != SVGT_ASSOC_CLASSIC)
+        return fail(SVGT_ERR_ARG, "bad %s", "assoc_mode");
+    if (b->unit_mode < 0 || b->unit_mode > 2) return fail(SVGT_ERR_ARG, "bad %s", "unit_mode");
+    if (b->n_sites / 32 >= 0x7fffffffLL) return fail(SVGT_ERR_ARG, "too many %s", "sites");
+    const uintptr_t align = (uintptr_t)b->sites | (uintptr_t)b->rows | (uintptr_t)b->lib_i32 | (uintptr_t)b->out_final;
+    if (align & 15) return fail(SVGT_ERR_ARG, "%s must be 16-byte aligned", "row arrays");
+    return SVGT_OK;
+}
+
+int svgt_score_compact(const svgt_cbatch_t *b, void *out_rows, int32_t *status, void *stream)
+{
+    int rc = check_cbatch(b);
+    if (rc != SVGT_OK) return rc;
+    if (!status || (b->n_sites > 0 && !out_rows)) return fail(SVGT_ERR_ARG, "null %s", "out_rows/status");
+    if ((uintptr_t)out_rows & 15) return fail(SVGT_ERR_ARG, "%s must be 16-byte aligned", "out_rows");
+    if (svgt_device_count() <= 0) return fail(SVGT_ERR_NO_DEVICE, "no CUDA device%s", nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(status)");
+    if (b->n_sites == 0 && !b->done_flag) return SVGT_OK;
+
+    SvgtCompactParams cp;
+    memset(&cp, 0, sizeof(cp));
+    SvgtParams &p = cp.base;
+    p.n_sites = b->n_sites;
+    p.order = b->order;
+    p.lib_f64 = b->lib_f64; p.lib_i32 = (const int4 *)b->lib_i32; p.n_lib = b->n_lib;
+    p.hist = b->hist; p.n_hist = b->n_hist;
+    p.pm = b->pm; p.logt = b->logt; p.n_log = b->n_log; p.consts = b->consts;
+    p.min_aligned = b->min_aligned; p.split_slop = b->split_slop; p.assoc_mode = b->assoc_mode;
+    p.split_weight = b->split_weight; p.disc_weight = b->disc_weight;
+    p.out = (svgt_out_row_t *)out_rows;
+    p.status = status;
+    cp.sites = (const int4 *)b->sites;
+    cp.rows = (const int4 *)b->rows; cp.n_rows = b->n_rows;
+    cp.out_final = (svgt_out_row_t *)b->out_final;
+    cp.done_flag = b->done_flag; cp.done_value = b->done_value;
+    cp.hist_max = b->hist_max;
+    e = (cudaError_t)svgt_launch_compact(cp, b->unit_mode, st);
+    if (e != cudaSuccess) return cuda_fail(e, "svgt_compact_kernel launch");
+    return SVGT_OK;
+}
+
+static void ctx_sync_all(svgt_ctx *c)
+{
+    cudaStreamSynchronize(c->s_h2d);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->s_d2h);
+}
+
+static int64_t csite_off(const int32_t *row) { return (int64_t)(uint32_t)row[8] | ((int64_t)row[9] << 32); }
+
+/*
+ * Pipelined host path for large compact batches whose rows are laid out in site order
+ * (SVGT_LAYOUT_SITE_ORDER): the sites are cut into kSlices contiguous slices; slice k's site rows and
+ * evidence rows go up on the H2D stream while slice k-1 is scored and slice k-2's result rows come back on
+ * the D2H stream.  Slice boundaries are validated on the host before anything is queued; every error exit
+ * drains the three streams first, so no copy is still reading or writing the caller's buffers when the
+ * call returns.
+ */
+static int ctx_score_pipelined_compact(svgt_ctx *c, const svgt_cbatch_t *hb, void *out_rows_host)
+{
+    const int64_t n = hb->n_sites;
+    int64_t cut_s[kSlices + 1], cut_r[kSlices + 1];
+    for (int k = 0; k <= kSlices; ++k) {
+        cut_s[k] = n * k / kSlices;
+        cut_r[k] = cut_s[k] < n ? csite_off(hb->sites + cut_s[k] * SVGT_CSITE_WORDS) : hb->n_rows;
+        if (cut_r[k] < 0 || cut_r[k] > hb->n_rows || (k > 0 && cut_r[k] < cut_r[k - 1]))
+            return fail(SVGT_ERR_ARG, "%s: row offsets are not in site order", "SVGT_LAYOUT_SITE_ORDER");
+    }
+    if (cut_r[0] != 0) return fail(SVGT_ERR_ARG, "%s: the first site's rows do not start at 0", "SVGT_LAYOUT_SITE_ORDER");
+    int rc = SVGT_OK;
+    cudaError_t e = cudaSuccess;
+    svgt_cbatch_t db = *hb;
+#define UPS(slot, field, type, count)                                                         \
+    do {                                                                                      \
+        const size_t bytes_ = (size_t)(count) * sizeof(type);                                 \
+        if ((rc = ctx_reserve(c, slot, bytes_)) != SVGT_OK) goto fail_out;                    \
+        if (bytes_) {                                                                         \
+            e = cudaMemcpyAsync(c->buf[slot], hb->field, bytes_, cudaMemcpyHostToDevice, c->s_h2d); \
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); goto fail_out; } \
+            c->h2d += (int64_t)bytes_;                                                        \
+        }                                                                                     \
+        db.field = (const type *)c->buf[slot];                                                \
+    } while (0)
+    UPS(B_LIBF, lib_f64, double, hb->n_lib * 4);
+    UPS(B_LIBI, lib_i32, int32_t, hb->n_lib * 4);
+    UPS(B_HIST, hist, uint32_t, hb->n_hist);
+    UPS(B_PM, pm, double, 256);
+    UPS(B_LOG, logt, double, hb->n_log);
+    UPS(B_CONSTS, consts, double, 32);
+#undef UPS
+    if ((rc = ctx_reserve(c, B_SITES, (size_t)n * SVGT_CSITE_WORDS * 4)) != SVGT_OK) goto fail_out;
+    if ((rc = ctx_reserve(c, B_FRAGS, (size_t)hb->n_rows * SVGT_CROW_WORDS * 4)) != SVGT_OK) goto fail_out;
+    if ((rc = ctx_reserve(c, B_OUT, (size_t)n * SVGT_OUT_BYTES)) != SVGT_OK) goto fail_out;
+    if ((rc = ctx_reserve(c, B_STATUS, 16 * kSlices)) != SVGT_OK) goto fail_out;
+    db.order = nullptr;                               /* the launch permutation spans the whole batch */
+    db.rows = (const int32_t *)c->buf[B_FRAGS];
+    for (int k = 0; k < kSlices; ++k) {
+        const int64_t s0 = cut_s[k], s1 = cut_s[k + 1];
+        const size_t bs = (size_t)(s1 - s0) * SVGT_CSITE_WORDS * 4, br = (size_t)(cut_r[k + 1] - cut_r[k]) * SVGT_CROW_WORDS * 4;
+        if (bs && (e = cudaMemcpyAsync((char *)c->buf[B_SITES] + (size_t)s0 * SVGT_CSITE_WORDS * 4,
+                                       hb->sites + s0 * SVGT_CSITE_WORDS, bs, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess) {
+            rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); goto fail_out;
+        }
+        if (br && (e = cudaMemcpyAsync((char *)c->buf[B_FRAGS] + (size_t)cut_r[k] * SVGT_CROW_WORDS * 4,
+                                       hb->rows + cut_r[k] * SVGT_CROW_WORDS, br, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess) {
+            rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); goto fail_out;
+        }
+        c->h2d += (int64_t)(bs + br);
+        cudaEventRecord(c->up[k], c->s_h2d);
+        if (s1 == s0) continue;
+        cudaStreamWaitEvent(c->stream, c->up[k], 0);
+        svgt_cbatch_t sb = db;
+        sb.sites = (const int32_t *)c->buf[B_SITES] + s0 * SVGT_CSITE_WORDS;
+        sb.n_sites = s1 - s0; sb.n_rows = cut_r[k + 1];  /* a site whose rows lie beyond the uploaded prefix is a real error */
+        cudaEventRecord(c->k0[k], c->stream);
+        rc = svgt_score_compact(&sb, (char *)c->buf[B_OUT] + (size_t)s0 * SVGT_OUT_BYTES, (int32_t *)c->buf[B_STATUS] + 4 * k,
+                                c->stream);
+        if (rc != SVGT_OK) goto fail_out;
+        cudaEventRecord(c->k1[k], c->stream);
+        cudaStreamWaitEvent(c->s_d2h, c->k1[k], 0);
+        e = cudaMemcpyAsync((char *)out_rows_host + (size_t)s0 * SVGT_OUT_BYTES, (char *)c->buf[B_OUT] + (size_t)s0 * SVGT_OUT_BYTES,
+                            (size_t)(s1 - s0) * SVGT_OUT_BYTES, cudaMemcpyDeviceToHost, c->s_d2h);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); goto fail_out; }
+        c->d2h += (s1 - s0) * (int64_t)SVGT_OUT_BYTES;
+    }
+    {
+        int32_t status[4 * kSlices];
+        memset(status, 0, sizeof(status));
+        cudaStreamWaitEvent(c->s_d2h, c->k1[kSlices - 1], 0);
+        e = cudaMemcpyAsync(status, c->buf[B_STATUS], sizeof(status), cudaMemcpyDeviceToHost, c->s_d2h);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(status)"); goto fail_out; }
+        c->d2h += (int64_t)sizeof(status);
+        if ((e = cudaStreamSynchronize(c->s_d2h)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamSynchronize"); goto fail_out; }
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamSynchronize"); goto fail_out; }
+        c->kernel_ms = 0.f;
+        int first = 0, count = 0;
+        for (int k = 0; k < kSlices; ++k) {
+            if (cut_s[k + 1] == cut_s[k]) continue;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->k0[k], c->k1[k]);
+            c->kernel_ms += ms;
+            if (status[4 * k] != 0 && first == 0) first = status[4 * k];
+            count += status[4 * k + 2];
+        }
+        if (first != 0) {
+            char msg[64];
+            snprintf(msg, sizeof(msg), "%d site(s), first code %d", count, first);
+            return fail(first, "scoring kernel flagged %s", msg);
+        }
+    }
+    return SVGT_OK;
+fail_out:
+    ctx_sync_all(c);
+    return rc;
+}
+
+int svgt_ctx_score_host_compact(svgt_ctx_t *c, const svgt_cbatch_t *hb, void *out_rows_host)
+{
+    if (!c) return fail(SVGT_ERR_ARG, "null %s", "ctx");
+    int rc = check_cbatch(hb);
+    if (rc != SVGT_OK) return rc;
+    if (hb->out_final || hb->done_flag) return fail(SVGT_ERR_ARG, "%s must be NULL on the host path", "out_final/done_flag");
+    if (hb->n_sites > 0 && !out_rows_host) return fail(SVGT_ERR_ARG, "null %s", "out_rows_host");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    c->h2d = c->d2h = 0;
+    c->kernel_ms = 0.f;
+
+    /* large batches in site order: overlap the copies with the kernels (SVGT_PIPELINE_MIN_SITES overrides
+     * the threshold, 0 disables) */
+    static const long long min_sites = [] {
+        const char *v = getenv("SVGT_PIPELINE_MIN_SITES");
+        return v && *v ? atoll(v) : 131072LL;
+    }();
+    if (min_sites > 0 && hb->n_sites >= min_sites && hb->n_sites >= kSlices && (hb->flags & SVGT_LAYOUT_SITE_ORDER))
+        return ctx_score_pipelined_compact(c, hb, out_rows_host);
+
+    svgt_cbatch_t db = *hb;
+#define UP(slot, field, type, count)                                                          \
+    do {                                                                                      \
+        rc = ctx_upload(c, slot, hb->field, (size_t)(count) * sizeof(type));                  \
+        if (rc != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }                   \
+        db.field = (const type *)c->buf[slot];                                                \
+    } while (0)
+    UP(B_SITES, sites, int32_t, hb->n_sites * SVGT_CSITE_WORDS);
+    UP(B_FRAGS, rows, int32_t, hb->n_rows * SVGT_CROW_WORDS);
+    if (hb->order) UP(B_ORDER, order, int32_t, hb->n_sites);
+    UP(B_LIBF, lib_f64, double, hb->n_lib * 4);
+    UP(B_LIBI, lib_i32, int32_t, hb->n_lib * 4);
+    UP(B_HIST, hist, uint32_t, hb->n_hist);
+    UP(B_PM, pm, double, 256);
+    UP(B_LOG, logt, double, hb->n_log);
+    UP(B_CONSTS, consts, double, 32);
+#undef UP
+    if ((rc = ctx_reserve(c, B_OUT, (size_t)hb->n_sites * SVGT_OUT_BYTES)) != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
+    if ((rc = ctx_reserve(c, B_STATUS, 16)) != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
+
+    cudaEventRecord(c->ev0, c->stream);
+    rc = svgt_score_compact(&db, c->buf[B_OUT], (int32_t *)c->buf[B_STATUS], c->stream);
+    if (rc != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
+    cudaEventRecord(c->ev1, c->stream);
+
+    int32_t status[4] = {0, 0, 0, 0};
+    if (hb->n_sites > 0) {
+        e = cudaMemcpyAsync(out_rows_host, c->buf[B_OUT], (size_t)hb->n_sites * SVGT_OUT_BYTES,
+                            cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) { cudaStreamSynchronize(c->stream); return cuda_fail(e, "cudaMemcpyAsync(D2H)"); }
+        c->d2h += hb->n_sites * (int64_t)SVGT_OUT_BYTES;
+    }
+    e = cudaMemcpyAsync(status, c->buf[B_STATUS], sizeof(status), cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) { cudaStreamSynchronize(c->stream); return cuda_fail(e, "cudaMemcpyAsync(status)"); }
+    c->d2h += (int64_t)sizeof(status);
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    cudaEventElapsedTime(&c->kernel_ms, c->ev0, c->ev1);
+    if (status[0] != 0) {
+        char msg[64];
+        snprintf(msg, sizeof(msg), "%d site(s), first code %d", status[2], status[0]);
+        return fail(status[0], "scoring kernel flagged %s", msg);
+    }
+    return SVGT_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* peer-visible buffers (multi-GPU output without a collective)                          */
+/* ------------------------------------------------------------------------------------ */
+int svgt_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[64])
+{
+    if (!dev_ptr || !handle || bytes <= 0) return fail(SVGT_ERR_ARG, "bad %s", "svgt_shared_alloc arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void *ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, (size_t)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(shared)");
+    if ((e = cudaMemset(ptr, 0, (size_t)bytes)) != cudaSuccess) { cudaFree(ptr); return cuda_fail(e, "cudaMemset(shared)"); }
+    cudaIpcMemHandle_t h;
+    if ((e = cudaIpcGetMemHandle(&h, ptr)) != cudaSuccess) { cudaFree(ptr); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle, &h, 64);
+    *dev_ptr = ptr;
+    return SVGT_OK;
+}
+
+int svgt_shared_open(const unsigned char handle[64], void **dev_ptr)
+{
+    if (!dev_ptr || !handle) return fail(SVGT_ERR_ARG, "bad %s", "svgt_shared_open arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    *dev_ptr = ptr;
+    return SVGT_OK;
+}
+
+int svgt_shared_close(void *dev_ptr)
+{
+    if (!dev_ptr) return SVGT_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+
+int svgt_shared_free(void *dev_ptr)
+{
+    if (!dev_ptr) return SVGT_OK;
+    cudaError_t e = cudaFree(dev_ptr);
+    return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "cudaFree(shared)");
 }
 
 int svgt_ctx_last_traffic(const svgt_ctx_t *c, int64_t *h2d_bytes, int64_t *d2h_bytes)

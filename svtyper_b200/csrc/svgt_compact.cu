@@ -1,0 +1,556 @@
+/*
+ * svgt_compact.cu -- the default tally kernel: compact 16-byte evidence rows (svtyper_b200/compact.py)
+ * delivered by TMA bulk copies, scored one row per lane, summed in order one chain per lane
+ * (reference singlesample.py:355-404: tally_variant_read_fragments; classic.py:286-435).
+ *
+ * Mapping (one persistent CTA per SM, work units claimed from an atomic cursor):
+ *   - a warp owns a unit of up to G = 8 sites of the work-descending launch order and walks them in
+ *     lock step: super-step k covers rows [32k, 32k + 32) of every site that still has rows -- first the
+ *     fragment rows of the sites, then their split rows;
+ *   - row delivery: at the start of super-step k lanes 0..G-1 each issue ONE cp.async.bulk (TMA 1-D,
+ *     <= 512 bytes, global -> shared) for THEIR site's rows of super-step k + 1 into the other half of a
+ *     two-slot ring, all G copies signalling one mbarrier whose transaction count lane 0 armed with the
+ *     summed byte count.  The warp polls that barrier once per super-step and each lane then reads its row
+ *     with one conflict-free LDS.128.  No per-lane copy instructions, no registers or scoreboards held by
+ *     rows in flight, a whole super-step (2-3 us of scoring) of prefetch distance;
+ *   - phase A (score_cfrag_chunk / score_csplit_chunk): one row per lane, straight-line predicate chain,
+ *     three doubles {a + b, p_ref, p_alt} parked structure-of-arrays in shared memory;
+ *   - phase B after each super-step: lane 4g + c replays chain c of site g over the <= 32 parked rows in
+ *     row order (the fp64 sums are order-sensitive: SURVEY.md H1), 3 G chains side by side;
+ *   - the five sums of a site are parked in its 80-byte row of `out`; svgt_call_compact_kernel (one site
+ *     per thread) applies the zeroing rules and bayesian_genotype (singlesample.py:382-473) and writes the
+ *     final row -- to `out`, or to `out_final` when the caller supplies one (a peer-mapped buffer on
+ *     another GPU: the multi-GPU gather without a collective).
+ */
+#include "svgt_compact.cuh"
+
+namespace {
+
+#ifndef SVGT_C_THREADS
+#define SVGT_C_THREADS 448          /* 14 warps: 13.8 KB of per-warp state each + the per-CTA tables fill the 227 KB */
+#endif
+#ifndef SVGT_C_G
+#define SVGT_C_G 8
+#endif
+#ifndef SVGT_C_DEPTH
+#define SVGT_C_DEPTH 2              /* super-step slots in the ring */
+#endif
+constexpr int kCD = SVGT_C_DEPTH;
+constexpr int kCWarps = SVGT_C_THREADS / 32;
+constexpr int kCHistPad = 8;
+
+template <int G>
+struct alignas(128) CWarpSmem {
+    int4 ring[kCD][G][33];          /* TMA destinations: [slot][site][row]; once a lane has read its row, the same 16
+                                       bytes park {p_ref, p_alt} (or {alt_seq, alt_clip}) for phase B.  33-row
+                                       stride: the chain lanes of different sites read distinct banks */
+    double spark[G][33];            /* parked a + b (or the two LUT indices where phase B needs a and b apart) */
+    unsigned long long bar[kCD];    /* one mbarrier per slot */
+    int cnt[2][8];                  /* [0] fragment rows, [1] split rows of each site (uniform reads) */
+    SiteS site[G];
+    CSiteF sf[G];
+    CSplitF spf[G];
+    WinF wf[G][kWLibs + 1];
+    Win gwin[kWLibs];               /* windows of the non-fast site being scored */
+    double zero[2];
+};
+
+/* shared memory left for the cached histogram counts once the per-warp state and the per-CTA tables are placed */
+constexpr size_t kCFixedBytes = ((512 * sizeof(double) + SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF) + 127) & ~(size_t)127) +
+                                sizeof(CWarpSmem<SVGT_C_G>) * kCWarps;
+constexpr size_t kCSmemLimit = 227 * 1024;
+static_assert(kCFixedBytes + 4096 <= kCSmemLimit, "per-warp state does not fit the SM's shared memory");
+constexpr long long kCHistWordsMax = (long long)((kCSmemLimit - kCFixedBytes) / 4) - kCHistPad;
+
+__host__ __device__ __forceinline__ long long c_hist_words(long long n_hist)
+{
+    return (n_hist < kCHistWordsMax ? n_hist : kCHistWordsMax) + kCHistPad;
+}
+
+/* unit ramp (see svgt_lean.cu: the heaviest sites are spread one per warp for small batches) */
+struct CUnit { long long base; int count; };
+
+template <int G>
+__host__ __device__ __forceinline__ CUnit c_unit_range(long long unit, long long W, int ramp)
+{
+    CUnit r;
+    if (!ramp || G < 8) { r.base = unit * G; r.count = G; return r; }
+    if (unit < W) { r.base = unit; r.count = 1; }
+    else if (ramp == 2) { r.base = W + (unit - W) * 8; r.count = 8; }
+    else if (unit < 2 * W) { r.base = W + (unit - W) * 2; r.count = 2; }
+    else if (unit < 3 * W) { r.base = 3 * W + (unit - 2 * W) * 4; r.count = 4; }
+    else { r.base = 7 * W + (unit - 3 * W) * 8; r.count = 8; }
+    return r;
+}
+
+template <int G>
+__host__ __device__ __forceinline__ long long c_n_units(long long n_sites, long long W, int ramp)
+{
+    if (!ramp || G < 8) return (n_sites + G - 1) / G;
+    if (n_sites <= W) return n_sites;
+    if (ramp == 2) return W + (n_sites - W + 7) / 8;
+    if (n_sites <= 3 * W) return W + (n_sites - W + 1) / 2;
+    if (n_sites <= 7 * W) return 2 * W + (n_sites - 3 * W + 3) / 4;
+    return 3 * W + (n_sites - 7 * W + 7) / 8;
+}
+
+__device__ __forceinline__ unsigned c_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+/* non-fast sites (a breakend within min_aligned of the contig start): the wide-row cooperative scorer on
+ * decoded rows, out of line */
+struct CGenericOut { FragOut fo; unsigned carryA, carryB; int err; };
+
+template <int ASSOC>
+__device__ __noinline__ CGenericOut c_generic_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const Win *wins,
+                                                    const double *s_pm, const LibK *s_lib, const int lane, const int n,
+                                                    const int g, const int m, const int4 r, unsigned carryA,
+                                                    unsigned carryB, int err)
+{
+    int4 lo, hi;
+    decode_wide(r, S.tB, lo, hi);
+    if (lane >= n) { lo = make_int4(0, 0, 0, 0); hi = lo; }
+    CGenericOut q;
+    q.fo = score_frag_chunk<ASSOC>(p, t, S, wins, s_pm, s_lib, p.hist, lane, n, g, m, lo, hi, carryA, carryB, err);
+    q.carryA = carryA; q.carryB = carryB; q.err = err;
+    return q;
+}
+
+/* phase B of one fragment chunk for chain c (0 ref_seq: `s`, 8-byte stride; 1 ref_span / 2 alt_span: the two
+ * halves of the 16-byte parked rows `pr`); same replay as replay_frag_soa() */
+template <int ASSOC>
+__device__ __forceinline__ void c_replay_frag(const double *s, const double *pr, int c, int cnt, int lead, const double *s_pm,
+                                              double &acc, double &pend)
+{
+    const int2 *pi = reinterpret_cast<const int2 *>(s);                 /* .x = ia, .y = ib */
+    const double *px = c == 0 ? s : pr + (c - 1);
+    const int st = c == 0 ? 1 : 2;
+    if (cnt <= 0) return;
+    lead = lead < cnt ? lead : cnt;
+    if (ASSOC == SVGT_ASSOC_CLASSIC) {
+        if (c == 0) {
+            for (int j = 0; j < cnt; ++j) {
+                const int2 ix = pi[j];
+                acc = __dadd_rn(__dadd_rn(acc, s_pm[ix.x]), s_pm[ix.y]);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 2]);
+        }
+    } else {
+        for (int j = 0; j < lead; ++j) {                /* rows continuing the previous chunk's last fragment */
+            if (c == 0) {
+                const int2 ix = pi[j];
+                pend = __dadd_rn(__dadd_rn(pend, s_pm[ix.x]), s_pm[ix.y]);
+            } else {
+                pend = __dadd_rn(pend, px[j * 2]);
+            }
+        }
+#pragma unroll 8
+        for (int j = lead; j < cnt; ++j) {
+            acc = __dadd_rn(acc, pend);
+            pend = px[j * st];
+        }
+    }
+}
+
+/* phase B of one split chunk for chain c (0 alt_seq, 1 alt_clip) */
+template <int ASSOC>
+__device__ __forceinline__ void c_replay_split(const double *pr, int c, int cnt, int lead, double &acc, double &pend)
+{
+    const double *px = pr + c;
+    if (cnt <= 0) return;
+    lead = lead < cnt ? lead : cnt;
+    if (ASSOC == SVGT_ASSOC_CLASSIC) {
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 2]);
+    } else {
+        for (int j = 0; j < lead; ++j) pend = __dadd_rn(pend, px[j * 2]);
+#pragma unroll 8
+        for (int j = lead; j < cnt; ++j) {
+            acc = __dadd_rn(acc, pend);
+            pend = px[j * 2];
+        }
+    }
+}
+
+template <int G, int ASSOC>
+__global__ void __launch_bounds__(SVGT_C_THREADS, 1) svgt_compact_kernel(const SvgtCompactParams cp)
+{
+    typedef CWarpSmem<G> WS;
+    const SvgtParams &p = cp.base;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_pm = reinterpret_cast<double *>(smem_raw);
+    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 512);     /* pm[0..255], then pm[q] / 2 (generic scorer) */
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
+    LibF *s_libf = reinterpret_cast<LibF *>(smem_raw + off);
+    off += (kWLibs + 1) * sizeof(LibF);
+    off = (off + 127) & ~(size_t)127;
+    WS *s_warp = reinterpret_cast<WS *>(smem_raw + off);
+    off += sizeof(WS) * kCWarps;
+    unsigned *s_hist = reinterpret_cast<unsigned *>(smem_raw + off);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    int err = 0;
+    const int nl = p.n_lib < SVGT_SMEM_LIBS ? p.n_lib : SVGT_SMEM_LIBS;
+    for (int i = tid; i < 256; i += SVGT_C_THREADS) {
+        const double v = p.pm[i];
+        s_pm[i] = v;
+        s_pm[256 + i] = __dmul_rn(v, 0.5);
+    }
+    for (int i = tid; i < nl; i += SVGT_C_THREADS) s_lib[i] = derive_lib(p, i, &err);
+    WS &ws = s_warp[warp];
+    if (lane < 2) ws.zero[lane] = 0.0;
+    if (lane < kCD) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c_smem(&ws.bar[lane])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    /* the 32-bit form of 19 * h1 > h2 needs every histogram count below 2^26: the host states the largest
+     * count (svgt_cbatch_t::hist_max); 0 = unknown, then the CTA looks for itself */
+    bool small_counts;
+    if (cp.hist_max != 0u) { small_counts = cp.hist_max < (1u << 26); __syncthreads(); }
+    else {
+        int big = 0;
+        for (long long i = tid; i < p.n_hist; i += SVGT_C_THREADS) big |= p.hist[i] >= (1u << 26);
+        small_counts = __syncthreads_or(big) == 0;
+    }
+    if (tid == 0) {
+        const long long cap = c_hist_words(p.n_hist);
+        long long base = 0;
+        for (int l = 0; l <= kWLibs; ++l) {
+            LibF f; f.addr = 0u; f.len = 0; f.ok = 0; f.pad = 0;
+            if (l < kWLibs && l < nl) {
+                const LibK &L = s_lib[l];
+                const bool fits = L.hist_len < (1 << kHistLenBits) && base + L.hist_len + 1 <= cap;
+                if (L.safe && small_counts && fits) {
+                    f.addr = c_smem(s_hist + base); f.len = L.hist_len; f.ok = 1;
+                    base += L.hist_len + 1;
+                }
+            }
+            s_libf[l] = f;
+        }
+    }
+    __syncthreads();
+    for (int l = 0; l < kWLibs; ++l) {
+        const LibF f = s_libf[l];
+        if (!f.ok) continue;
+        unsigned *dst = s_hist + ((f.addr - c_smem(s_hist)) >> 2);
+        const unsigned *src = p.hist + s_lib[l].hist_off;
+        for (int i = tid; i <= f.len; i += SVGT_C_THREADS) dst[i] = i < f.len ? src[i] : 0u;
+    }
+    __syncthreads();
+
+    Tables t;
+    t.pm = s_pm; t.libs = s_lib; t.hist = p.hist;
+    t.conc = p.consts[C_CONC]; t.disc = p.consts[C_DISC];
+    const int m = p.min_aligned, slop = p.split_slop;
+    const unsigned zero_addr = c_smem(&ws.zero[0]);
+    const unsigned ring0 = c_smem(&ws.ring[0][0][0]);
+    const unsigned bars = c_smem(&ws.bar[0]);
+
+    const int gb = lane >> 2, c = lane & 3;                 /* phase-B role: chain c of site gb */
+    const int ramp = cp.ramp;
+    const long long W = (long long)gridDim.x * kCWarps;
+    const long long n_units = c_n_units<G>(p.n_sites, W, ramp);
+    unsigned tt = 0u;                                       /* super-steps consumed by this warp (slot / phase) */
+
+    long long unit = 0, unit_next = 0;
+    if (lane == 0) unit = (long long)atomicAdd(reinterpret_cast<unsigned *>(p.status + 1), 1u);
+    unit = __shfl_sync(full, unit, 0);
+    for (; unit < n_units; unit = __shfl_sync(full, unit_next, 0)) {
+        /* ---- lanes 0..G-1 read their site row and publish the scalars ---- */
+        int my_nf = 0, my_ns = 0;
+        const int4 *my_rows = cp.rows;
+        {
+            const CUnit ur = c_unit_range<G>(unit, W, ramp);
+            const long long idx = ur.base + lane;
+            const bool valid = lane < ur.count && lane < G && idx < p.n_sites;
+            long long site = 0;
+            bool valid2 = valid;
+            if (valid) {
+                site = p.order ? (long long)p.order[idx] : idx;
+                if (site < 0 || site >= p.n_sites) { site = 0; valid2 = false; err = SVGT_ERR_ARG; }   /* bad order[] entry */
+            }
+            int4 a = make_int4(0, 0, 0, 0), b = a, d = a;
+            if (valid2) {
+                const int4 *sp = cp.sites + site * 3;
+                a = ldg4(sp); b = ldg4(sp + 1); d = ldg4(sp + 2);
+            }
+            /* a = posA posB ciA0 ciA1; b = ciB0 ciB1 var_length meta; d = row_off(lo, hi) n_frag n_split */
+            const int meta = b.w;
+            const int4 cis = make_int4(b.x, b.y, 0, 0);
+            const bool ranged = site_fields_in_range(a, cis, m, slop);
+            const bool run = valid2 && !(meta & SITE_SKIP) && ranged;
+            const long long roff = ((long long)(unsigned)d.x) | ((long long)d.y << 32);
+            int nf = run ? d.z : 0, ns = run ? d.w : 0;
+            if (nf < 0 || ns < 0 || roff < 0 || roff + nf + ns > cp.n_rows) { nf = 0; ns = 0; err = SVGT_ERR_ARG; }
+            my_nf = nf; my_ns = ns; my_rows = cp.rows + roff;
+            if (lane < G) {
+                SiteS &S = ws.site[lane];
+                const int same = (meta >> 5) & 1;
+                S.tA = 0; S.tB = same ? 0 : 1;            /* invented contig ids: rows carry class bits */
+                S.wA0 = a.x - m; S.wA1 = a.x + m; S.wB0 = a.y - m; S.wB1 = a.y + m;
+                S.meta = (meta & 15) | ((a.x - m >= 0) << 8) | ((a.y - m >= 0) << 9);
+                S.var_length = b.z;
+                S.posA = a.x; S.posB = a.y; S.ciA0 = a.z; S.ciA1 = a.w; S.ciB0 = b.x; S.ciB1 = b.y;
+                S.dAB = a.y - a.x; S.nf = nf; S.foff = roff; S.soff = roff + nf; S.ns = ns;
+                S.slot = valid2 ? (int)site : -1;
+                S.pad1 = 0; S.pad2 = 0;
+                CSiteF &F = ws.sf[lane];
+                const int svtype = meta & 3;
+                F.wA0 = a.x - m; F.wA1 = a.x + m; F.wB0 = a.y - m; F.wB1 = a.y + m;
+                F.pat = (int)(CF_PAIRED | ((meta & SITE_O1_REV) ? CF_REV_A : 0u) | ((meta & SITE_O2_REV) ? CF_REV_B : 0u));
+                F.del = svtype == SV_DEL;
+                const bool okwin = (a.x - m >= 0) && (a.y - m >= 0);
+                F.fast = !okwin ? 0 : (svtype != SV_INV && same) ? 1 : 2;
+                F.m21 = 2 * m - 1;
+                F.sgnA = (meta & SITE_O1_REV) ? 1 : -1; F.sgnB = (meta & SITE_O2_REV) ? 1 : -1;
+                F.inv = svtype == SV_INV; F.same = same;
+                ws.spf[lane] = make_csplitf(S, slop);
+                ws.cnt[0][lane] = nf; ws.cnt[1][lane] = ns;
+            }
+            __syncwarp();
+            for (int i = lane; i < G * (kWLibs + 1); i += 32) {
+                const int g = i / (kWLibs + 1), l = i % (kWLibs + 1);
+                if (ws.site[g].nf && ws.sf[g].fast)
+                    ws.wf[g][l] = make_winf(ws.site[g], s_lib[l < nl ? l : 0], s_libf[l < nl ? l : kWLibs], m, zero_addr);
+            }
+            __syncwarp();
+        }
+        /* claim the next unit now: the atomic's round trip is hidden behind this unit's rows */
+        if (lane == 0) unit_next = (long long)atomicAdd(reinterpret_cast<unsigned *>(p.status + 1), 1u);
+
+        /* super-steps: nsf over fragment rows, then nss over split rows */
+        const int nsf = (__reduce_max_sync(full, my_nf) + 31) >> 5;
+        const int nss = (__reduce_max_sync(full, my_ns) + 31) >> 5;
+        const int T = nsf + nss;
+
+        /* lane g issues the bulk copy of site g's rows of super-step k into ring slot `slot` */
+        auto issue = [&](const int k, const unsigned slot) {
+            const bool sp = k >= nsf;
+            const int row0 = sp ? my_nf + (k - nsf) * 32 : k * 32;
+            const int end = sp ? my_nf + my_ns : my_nf;
+            int nrow = end - row0;
+            nrow = nrow < 0 ? 0 : (nrow > 32 ? 32 : nrow);
+            const unsigned bytes = (unsigned)nrow * 16u;
+            const unsigned total = __reduce_add_sync(full, bytes);
+            const unsigned bar = bars + slot * 8u;
+            /* the slot was last written by this warp's own parked rows (generic proxy): order them before the
+             * bulk copies (async proxy) that overwrite it */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+            __syncwarp();
+            if (bytes) {
+                const unsigned dst = ring0 + (slot * G + (unsigned)lane) * 528u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(my_rows + row0), "r"(bytes), "r"(bar) : "memory");
+            }
+        };
+
+        double sum_frag = 0.0, sum_split = 0.0;
+        double acc = 0.0, pend = 0.0;
+        unsigned carryA = 0u, carryB = 0u;
+        unsigned long long leads = 0ull;
+#pragma unroll 1
+        for (int k = 0; k < kCD - 1 && k < T; ++k) issue(k, (tt + (unsigned)k) % (unsigned)kCD);
+#pragma unroll 1
+        for (int k = 0; k < T; ++k, ++tt) {
+            const unsigned slot = tt % (unsigned)kCD;
+            if (k + kCD - 1 < T) issue(k + kCD - 1, (tt + (unsigned)(kCD - 1)) % (unsigned)kCD);
+            {
+                const unsigned bar = bars + slot * 8u, parity = (tt / (unsigned)kCD) & 1u;
+                unsigned ok;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                } while (!ok);
+            }
+            const bool sp = k >= nsf;
+            const int step = sp ? k - nsf : k;
+            const int *cnts = &ws.cnt[sp ? 1 : 0][0];
+            const unsigned slotaddr = ring0 + slot * (unsigned)(G * 528);
+            const unsigned rowaddr = slotaddr + (unsigned)lane * 16u;
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+                const int n = cnts[g] - step * 32;
+                if (n <= 0) continue;
+                int4 r;
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                             : "r"(rowaddr + (unsigned)g * 528u));
+                if (lane >= n) r = make_int4(0, 0, 0, 0);   /* the copy stopped at the site's last row */
+                if (!sp) {
+                    FragOut fo;
+                    if (ws.sf[g].fast) {
+                        fo = score_cfrag_chunk<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, n, g, m, r,
+                                                      carryA, carryB, err);
+                    } else {
+                        __syncwarp();
+                        if (lane < kWLibs) {
+                            if (lane < nl) ws.gwin[lane] = make_win(ws.site[g], s_lib[lane], m, small_counts);
+                            else ws.gwin[lane].flags = 0u;
+                        }
+                        __syncwarp();
+                        const CGenericOut q = c_generic_chunk<ASSOC>(p, t, ws.site[g], &ws.gwin[0], s_pm, s_lib, lane, n, g, m,
+                                                                     r, carryA, carryB, err);
+                        fo = q.fo; carryA = q.carryA; carryB = q.carryB; err = q.err;
+                    }
+                    /* park: {p_ref, p_alt} over the row just read, a + b (or the LUT index pair) beside it */
+                    double s0 = fo.s;
+                    if (ASSOC == SVGT_ASSOC_CLASSIC || (fo.lead > 0 && lane < fo.lead)) s0 = __hiloint2double(fo.ib, fo.ia);
+                    ws.spark[g][lane] = s0;
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowaddr + (unsigned)g * 528u), "d"(fo.p_ref), "d"(fo.p_alt) : "memory");
+                    if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
+                } else {
+                    const SplitOut so = score_csplit_chunk<ASSOC>(ws.spf[g], s_pm, lane, n, r);
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowaddr + (unsigned)g * 528u), "d"(so.vseq), "d"(so.vclip) : "memory");
+                    if (so.lead) leads |= (unsigned long long)so.lead << (8 * g);
+                }
+            }
+            /* ---- phase B: the ordered replay of this super-step's parked rows ---- */
+            __syncwarp();
+            if (gb < G && c < (sp ? 2 : 3)) {
+                int cnt = cnts[gb] - step * 32;
+                cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+                const int lead = (int)(leads >> (8 * gb)) & 0xFF;
+                const double *pr = reinterpret_cast<const double *>(&ws.ring[slot][gb][0]);
+                if (!sp) c_replay_frag<ASSOC>(&ws.spark[gb][0], pr, c, cnt, lead, s_pm, acc, pend);
+                else c_replay_split<ASSOC>(pr, c, cnt, lead, acc, pend);
+            }
+            leads = 0ull;
+            __syncwarp();
+            if (k == nsf - 1) {                             /* the fragment rows are done */
+                if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+                sum_frag = acc; acc = 0.0; pend = 0.0;
+            }
+        }
+        if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+        sum_split = acc;
+
+        /* ---- park the five sums in the site's output row (lane 4g+c holds chain c of site g) ---- */
+        if (gb < G && c < 3) {
+            const int site = ws.site[gb].slot;
+            if (site >= 0 && (ws.site[gb].nf | ws.site[gb].ns)) {
+                double *row = reinterpret_cast<double *>(p.out + site);
+                /* ParkedSums: ref_seq, alt_seq, alt_clip, ref_span, alt_span */
+                if (c == 0) { row[0] = sum_frag; row[1] = sum_split; }
+                else if (c == 1) { row[3] = sum_frag; row[2] = sum_split; }
+                else row[4] = sum_frag;
+            }
+        }
+        __syncwarp();
+    }
+    if (err) {
+        atomicCAS(p.status, 0, err);
+        atomicAdd(p.status + 2, 1);
+    }
+}
+
+/* one site per thread: zeroing rules + genotype call on the parked sums (compact site rows) */
+__global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompactParams cp)
+{
+    const SvgtParams &p = cp.base;
+    const long long site = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (site >= p.n_sites) return;
+    const int4 *sp = cp.sites + site * 3;
+    const int4 a = ldg4(sp), b = ldg4(sp + 1), d = ldg4(sp + 2);
+    const int meta = b.w;
+    int err = 0;
+    svgt_out_row_t o;
+    o.gl[0] = o.gl[1] = o.gl[2] = 0.0; o.sq = 0.0;
+    o.gt = 0; o.gq = 0; o.dp = 0; o.ro = 0; o.ao = 0; o.qr = 0; o.qa = 0;
+    o.rs = 0; o.as_ = 0; o.asc = 0; o.rp = 0; o.ap = 0;
+    if (meta & SITE_SKIP) { o.gt = SVGT_GT_SKIPPED; o.gq = -1; }
+    else if (!site_fields_in_range(a, make_int4(b.x, b.y, 0, 0), p.min_aligned, p.split_slop)) {
+        o.gt = SVGT_GT_BLANK; o.gq = -1; err = SVGT_ERR_RANGE;
+    } else {
+        ParkedSums s = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const long long roff = ((long long)(unsigned)d.x) | ((long long)d.y << 32);
+        const bool ok = !(d.z < 0 || d.w < 0 || roff < 0 || roff + d.z + d.w > cp.n_rows);
+        if (ok && (d.z > 0 || d.w > 0)) {
+            const double *row = reinterpret_cast<const double *>(p.out + site);
+            s.ref_seq = row[0]; s.alt_seq = row[1]; s.alt_clip = row[2]; s.ref_span = row[3]; s.alt_span = row[4];
+        }
+        Tables t;
+        t.pm = p.pm; t.libs = nullptr; t.hist = p.hist;
+        t.conc = 0.0; t.disc = 0.0;
+        call_site(p, t, meta & 3, s.ref_seq, s.alt_seq, s.alt_clip, s.ref_span, s.alt_span, o, err);
+    }
+    int4 *dst = reinterpret_cast<int4 *>((cp.out_final ? cp.out_final : p.out) + site);
+    const int4 *src = reinterpret_cast<const int4 *>(&o);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = src[i];
+    if (err) {
+        atomicCAS(p.status, 0, err);
+        atomicAdd(p.status + 2, 1);
+    }
+    /* multi-GPU: the last CTA to finish tells the gathering rank this shard's rows have landed */
+    if (cp.done_flag) {
+        __shared__ int last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(p.status + 3, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile int *>(cp.done_flag) = cp.done_value;
+            __threadfence_system();
+        }
+    }
+}
+
+template <int G>
+size_t c_smem_bytes(const SvgtParams &p)
+{
+    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF);
+    off = (off + 127) & ~(size_t)127;
+    off += sizeof(CWarpSmem<G>) * kCWarps;
+    off += (size_t)c_hist_words(p.n_hist) * sizeof(unsigned);
+    return off;
+}
+
+struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
+
+template <int G>
+int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream)
+{
+    static CLaunchInfo info[2] = {};
+    const SvgtParams &p = cp.base;
+    const int a = p.assoc_mode == SVGT_ASSOC_CLASSIC ? 1 : 0;
+    auto kern = a ? svgt_compact_kernel<G, SVGT_ASSOC_CLASSIC> : svgt_compact_kernel<G, SVGT_ASSOC_SSO>;
+    const size_t smem = c_smem_bytes<G>(p);
+    cudaError_t e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    CLaunchInfo &li = info[a];
+    const int di = dev & 15;
+    if (!li.ready[di] || li.smem_set[di] < smem) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return (int)e;
+        if ((e = cudaDeviceGetAttribute(&li.sms[di], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&li.per_sm[di], kern, SVGT_C_THREADS, smem)) != cudaSuccess)
+            return (int)e;
+        if (li.per_sm[di] < 1) li.per_sm[di] = 1;
+        li.smem_set[di] = smem; li.ready[di] = 1;
+    }
+    const long long cap = (long long)li.sms[di] * li.per_sm[di];      /* persistent: one resident wave */
+    const long long units = ramp ? p.n_sites : (p.n_sites + G - 1) / G;
+    const long long want = (units + kCWarps - 1) / kCWarps;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    if (ramp == 1 && p.n_sites >= 256 * cap * kCWarps) ramp = 0;       /* large batches amortise their longest unit */
+    SvgtCompactParams q = cp;
+    q.ramp = ramp;
+    kern<<<grid, SVGT_C_THREADS, smem, stream>>>(q);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    const int cgrid = (int)((p.n_sites + 255) / 256);
+    svgt_call_compact_kernel<<<cgrid, 256, 0, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int svgt_launch_compact(const SvgtCompactParams &cp, int unit_mode, cudaStream_t stream)
+{
+    /* unit_mode: 0 default (ramped units for small batches), 1 always G-site units, 2 two-site units */
+    if (unit_mode == 2) return launch_compact<2>(cp, 0, stream);
+    return launch_compact<SVGT_C_G>(cp, unit_mode == 0 ? 1 : 0, stream);
+}

@@ -1,0 +1,457 @@
+/*
+ * svgt_compact.cuh -- row scorers of the compact-schema tally kernel (svgt_compact.cu).
+ *
+ * Rows are 16 bytes (svtyper_b200/compact.py): a fragment row is {a_start, b_end, lenA | lenB | contig
+ * class, mapqA | mapqB | library | flags}; a split row is {l_start, r_start, lenL | lenR, mapqL | mapqR |
+ * flags | contig class}.  One LDS.128 per lane fetches a row; everything a row is tested against is
+ * warp-uniform per site (CSiteF, three LDS.128) or per (site, library) (WinF, two LDS.128).
+ *
+ * Same arithmetic as the wide-row scorers (reference citations in svgt_lean.cuh / svgt_coop.cuh); what
+ * changes with the encoding:
+ *   is_ref_seq (parsers.py:801-816)  a read [s, s + len) covers the window [w0, w0 + 2m) iff
+ *       (unsigned)(w0 - s) < max(len - 2m + 1, 0); for read B, stored by its end e,
+ *       (unsigned)(e - w1) < max(len - 2m + 1, 0).  Exact for every int32 input: a wrapped difference is
+ *       >= 2^30 while the bound is < 2^14.
+ *   contig tests (parsers.py:805,833-834)  are the four class bits of the row.
+ * Rows the 16-byte form cannot express directly (gapped reads, spans beyond 14 bits, extra primaries)
+ * arrive as EXTRA / MULTI / CONT rows and leave the straight-line chain through one vote, exactly as in
+ * the wide-row kernel; there they are decoded into the wide form (decode_wide) and handed to the same
+ * resolver / literal-path functions, so those are shared, not duplicated.
+ */
+#pragma once
+#include "svgt_lean.cuh"
+
+namespace {
+
+/* compact schema constants (svtyper_b200/compact.py) */
+enum : unsigned {
+    CS_SAME = 1u << 5,
+    CLS_A_ON_A = 1u << 28, CLS_A_ON_B = 1u << 29, CLS_B_ON_A = 1u << 30, CLS_B_ON_B = 1u << 31,
+    CF_PAIRED = 1u << 25, CF_REV_A = 1u << 26, CF_REV_B = 1u << 27, CF_CONT = 1u << 28, CF_EXTRA = 1u << 29,
+    CF_MULTI_A = 1u << 30, CF_MULTI_B = 1u << 31,
+    CSP_SOFT = 1u << 16, CSP_FIRST = 1u << 17, CSP_WIDE = 1u << 18, CSP_XEND = 1u << 19
+};
+constexpr int kLenBits = 14;
+constexpr unsigned kLenMask = (1u << kLenBits) - 1u;
+constexpr unsigned kLibMaskC = 0x1FFu;
+
+/* fast-site constants, three warp-uniform LDS.128 */
+struct CSiteF {
+    int wA0, wA1, wB0, wB1;
+    int pat, del, fast, m21;     /* pat: (w3 & 0x2E000000) of an alt-orientation pair; m21 = 2 * min_aligned - 1;
+                                    fast: 0 generic scorer, 1 one contig & not INV, 2 general chain */
+    int sgnA, sgnB, inv, same;
+};
+
+/* the wide form of a compact fragment row, with invented contig ids (0 = contig A, tB = contig B) */
+__device__ __forceinline__ void decode_wide(const int4 r, const int tB, int4 &lo, int4 &hi)
+{
+    const unsigned w2 = (unsigned)r.z, w3 = (unsigned)r.w;
+    const int tidA = (w2 & CLS_A_ON_A) ? 0 : ((w2 & CLS_A_ON_B) ? tB : -3);
+    const int tidB = (w2 & CLS_B_ON_A) ? 0 : ((w2 & CLS_B_ON_B) ? tB : -3);
+    int fl = ((w3 & CF_REV_A) ? F_REV_A : 0) | ((w3 & CF_REV_B) ? F_REV_B : 0) | ((w3 & CF_PAIRED) ? F_PAIRED : 0) |
+             ((w3 & CF_CONT) ? F_CONT : 0);
+    hi.z = (int)((w3 & 0xFFFFu) | (((w3 >> 16) & kLibMaskC) << 16));
+    if (w3 & CF_EXTRA) {
+        fl = F_EXTRA | (fl & F_CONT);
+        if (w3 & CF_MULTI_B) { lo = make_int4(0, 0, r.x, r.y); hi.x = 0; hi.y = tidB; fl |= F_HAS_B; }
+        else { lo = make_int4(r.x, r.y, 0, 0); hi.x = tidA; hi.y = 0; fl |= F_HAS_A; }
+        hi.z &= ~0xFFFF;
+    } else {
+        const int lenA = (int)(w2 & kLenMask), lenB = (int)((w2 >> kLenBits) & kLenMask);
+        const bool hasB = (w3 & CF_PAIRED) || (w2 & (CLS_B_ON_A | CLS_B_ON_B));
+        lo = make_int4(r.x, r.x + lenA, r.y - lenB, r.y);
+        hi.x = tidA; hi.y = tidB;
+        fl |= F_HAS_A | (hasB ? F_HAS_B : 0) | ((w3 & CF_MULTI_A) ? F_MULTI_A : 0) | ((w3 & CF_MULTI_B) ? F_MULTI_B : 0);
+    }
+    hi.w = fl;
+}
+
+/*
+ * One row of a fast site on one contig (not an inversion).  Outputs as in fast_row(): high words of the
+ * {0,1} factors of a and b, of the {0,.5,1} factor of p_ref and the {0,1} factor of p_alt, and `tie`.
+ *   %5 a_start  %6 b_end  %7 w2  %8 w3
+ *   %9..%12 wA0 wA1 wB0 wB1    %13 pat  %14 del  %15 m21
+ *   %16..%19 altA_lo altA_w1 altB_lo altB_w1    %20 FL  %21 FL1  %22 Lk  %23 hpk
+ */
+__device__ __forceinline__ void crow_fast(const int4 r, const int4 f0, const int4 f1, const uint4 w0, const uint4 w1,
+                                          double &hA, double &hB, double &wref, double &walt, int &tie)
+{
+    asm("{\n\t"
+        ".reg .pred eA, eB, p, q, hA, hB, pe0, pa, pr0, ra, rb, pc, pt, pdel, both, any, x1, ron, aon, ptrap;\n\t"
+        ".reg .b32 t, u, d, x, o, k2, len, hb, i1, i2, a1, a2, h1, h2, l19, zr, lmA, lmB;\n\t"
+        "mov.b32 zr, 0;\n\t"
+        /* span bounds: max(len - 2m + 1, 0) */
+        "and.b32 t, %7, 0x3FFF;\n\t"
+        "sub.s32 t, t, %15;\n\t"
+        "max.s32 lmA, t, 0;\n\t"
+        "bfe.u32 t, %7, 14, 14;\n\t"
+        "sub.s32 t, t, %15;\n\t"
+        "max.s32 lmB, t, 0;\n\t"
+        /* contig class: on the site's (single) contig */
+        "and.b32 t, %7, 0x10000000;\n\t"
+        "setp.ne.s32 eA, t, 0;\n\t"
+        "and.b32 t, %7, 0x40000000;\n\t"
+        "setp.ne.s32 eB, t, 0;\n\t"
+        /* is_ref_seq, read A then read B */
+        "sub.s32 u, %9, %5;\n\t"
+        "setp.lt.and.u32 p, u, lmA, eA;\n\t"
+        "sub.s32 u, %11, %5;\n\t"
+        "setp.lt.and.u32 q, u, lmA, eA;\n\t"
+        "or.pred hA, p, q;\n\t"
+        "sub.s32 u, %6, %10;\n\t"
+        "setp.lt.and.u32 p, u, lmB, eB;\n\t"
+        "sub.s32 u, %6, %12;\n\t"
+        "setp.lt.and.u32 q, u, lmB, eB;\n\t"
+        "or.pred hB, p, q;\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hA;\n\t"
+        "mov.b64 %0, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hB;\n\t"
+        "mov.b64 %1, {zr, t};\n\t"
+        /* paired-end straddles */
+        "and.pred pe0, eA, eB;\n\t"
+        "and.b32 t, %8, 0x2E000000;\n\t"
+        "setp.eq.and.s32 pa, t, %13, pe0;\n\t"
+        "setp.eq.and.s32 pr0, t, 0x0A000000, pe0;\n\t"
+        "sub.s32 d, %5, %16;\n\t"
+        "setp.lt.and.u32 pa, d, %17, pa;\n\t"
+        "sub.s32 d, %6, %18;\n\t"
+        "setp.lt.and.u32 pa, d, %19, pa;\n\t"
+        "add.s32 x, %5, %20;\n\t"
+        "sub.s32 d, x, %9;\n\t"
+        "setp.lt.and.u32 ra, d, %21, pr0;\n\t"
+        "sub.s32 d, %6, %10;\n\t"
+        "add.s32 d, d, -1;\n\t"
+        "setp.lt.and.u32 ra, d, %21, ra;\n\t"
+        "sub.s32 d, x, %11;\n\t"
+        "setp.lt.and.u32 rb, d, %21, pr0;\n\t"
+        "sub.s32 d, %6, %12;\n\t"
+        "add.s32 d, d, -1;\n\t"
+        "setp.lt.and.u32 rb, d, %21, rb;\n\t"
+        /* p_concordant on the counts; keys outside the histogram clamp onto the zero sentinel */
+        "sad.s32 o, %6, %5, 0;\n\t"
+        "sub.s32 k2, o, %22;\n\t"
+        "shr.u32 len, %23, 18;\n\t"
+        "and.b32 hb, %23, 0x3ffff;\n\t"
+        "min.u32 i1, o, len;\n\t"
+        "min.u32 i2, k2, len;\n\t"
+        "mad.lo.u32 a1, i1, 4, hb;\n\t"
+        "mad.lo.u32 a2, i2, 4, hb;\n\t"
+        "ld.shared.u32 h1, [a1];\n\t"
+        "ld.shared.u32 h2, [a2];\n\t"
+        "mul.lo.u32 l19, h1, 19;\n\t"
+        "setp.gt.u32 pc, l19, h2;\n\t"
+        "setp.eq.u32 pt, l19, h2;\n\t"
+        "setp.ne.and.u32 pt, h2, 0, pt;\n\t"
+        "setp.lt.s32 ptrap, %22, 0;\n\t"
+        "or.pred pt, pt, ptrap;\n\t"
+        "selp.s32 %4, 1, 0, pt;\n\t"
+        /* weights */
+        "setp.ne.s32 pdel, %14, 0;\n\t"
+        "and.pred both, ra, rb;\n\t"
+        "or.pred any, ra, rb;\n\t"
+        "and.pred x1, both, !pdel;\n\t"
+        "and.pred ron, any, !x1;\n\t"
+        "and.pred ron, ron, pc;\n\t"
+        "and.pred x1, pdel, pc;\n\t"
+        "and.pred aon, pa, !x1;\n\t"
+        "selp.b32 t, 0x3FF00000, 0x3FE00000, both;\n\t"
+        "selp.b32 t, t, 0, ron;\n\t"
+        "mov.b64 %2, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, aon;\n\t"
+        "mov.b64 %3, {zr, t};\n\t"
+        "}"
+        : "=d"(hA), "=d"(hB), "=d"(wref), "=d"(walt), "=r"(tie)
+        : "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w),                                                /* %5..%8   */
+          "r"(f0.x), "r"(f0.y), "r"(f0.z), "r"(f0.w), "r"(f1.x), "r"(f1.y), "r"(f1.w),           /* %9..%15  */
+          "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w) /* %16..%23 */);
+}
+
+/*
+ * The same row for a site whose breakends lie on two contigs and / or an inversion (fast_row_gen()):
+ *   %24 sgnA  %25 sgnB  %26 inv
+ */
+__device__ __forceinline__ void crow_gen(const int4 r, const int4 f0, const int4 f1, const int4 f2, const uint4 w0,
+                                         const uint4 w1, double &hA, double &hB, double &wref, double &walt, int &tie)
+{
+    asm("{\n\t"
+        ".reg .pred eaa, eab, eba, ebb, p, q, hA, hB, pe0, pa, prc, pr0, ra, rb, pc, pt, pdel, pinv, both, any, x1, ron, aon, ptrap;\n\t"
+        ".reg .b32 t, u, d, x, o, k2, len, hb, i1, i2, a1, a2, h1, h2, l19, zr, lmA, lmB;\n\t"
+        "mov.b32 zr, 0;\n\t"
+        "and.b32 t, %7, 0x3FFF;\n\t"
+        "sub.s32 t, t, %15;\n\t"
+        "max.s32 lmA, t, 0;\n\t"
+        "bfe.u32 t, %7, 14, 14;\n\t"
+        "sub.s32 t, t, %15;\n\t"
+        "max.s32 lmB, t, 0;\n\t"
+        "and.b32 t, %7, 0x10000000;\n\t"
+        "setp.ne.s32 eaa, t, 0;\n\t"
+        "and.b32 t, %7, 0x20000000;\n\t"
+        "setp.ne.s32 eab, t, 0;\n\t"
+        "and.b32 t, %7, 0x40000000;\n\t"
+        "setp.ne.s32 eba, t, 0;\n\t"
+        "and.b32 t, %7, 0x80000000;\n\t"
+        "setp.ne.s32 ebb, t, 0;\n\t"
+        /* is_ref_seq: on contig A against window A, on contig B against window B */
+        "sub.s32 u, %9, %5;\n\t"
+        "setp.lt.and.u32 p, u, lmA, eaa;\n\t"
+        "sub.s32 u, %11, %5;\n\t"
+        "setp.lt.and.u32 q, u, lmA, eab;\n\t"
+        "or.pred hA, p, q;\n\t"
+        "sub.s32 u, %6, %10;\n\t"
+        "setp.lt.and.u32 p, u, lmB, eba;\n\t"
+        "sub.s32 u, %6, %12;\n\t"
+        "setp.lt.and.u32 q, u, lmB, ebb;\n\t"
+        "or.pred hB, p, q;\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hA;\n\t"
+        "mov.b64 %0, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, hB;\n\t"
+        "mov.b64 %1, {zr, t};\n\t"
+        /* alt straddle: read A on contig A, read B on contig B, alt orientation; INV also the reciprocal one */
+        "and.pred pe0, eaa, ebb;\n\t"
+        "and.b32 t, %8, 0x2E000000;\n\t"
+        "setp.eq.and.s32 pa, t, %13, pe0;\n\t"
+        "sub.s32 d, %5, %16;\n\t"
+        "setp.lt.and.u32 pa, d, %17, pa;\n\t"
+        "sub.s32 d, %6, %18;\n\t"
+        "setp.lt.and.u32 pa, d, %19, pa;\n\t"
+        "setp.ne.s32 pinv, %26, 0;\n\t"
+        "and.pred prc, pe0, pinv;\n\t"
+        "xor.b32 u, %13, 0x0C000000;\n\t"
+        "setp.eq.and.s32 prc, t, u, prc;\n\t"
+        "sub.s32 d, %5, %16;\n\t"
+        "mad.lo.s32 d, %24, %20, d;\n\t"
+        "setp.lt.and.u32 prc, d, %17, prc;\n\t"
+        "sub.s32 d, %6, %18;\n\t"
+        "mad.lo.s32 d, %25, %20, d;\n\t"
+        "setp.lt.and.u32 prc, d, %19, prc;\n\t"
+        "or.pred pa, pa, prc;\n\t"
+        /* reference FR pairs: both reads on contig A around A, both on contig B around B */
+        "setp.eq.s32 pr0, t, 0x0A000000;\n\t"
+        "and.pred ra, eaa, eba;\n\t"
+        "and.pred ra, ra, pr0;\n\t"
+        "and.pred rb, eab, ebb;\n\t"
+        "and.pred rb, rb, pr0;\n\t"
+        "add.s32 x, %5, %20;\n\t"
+        "sub.s32 d, x, %9;\n\t"
+        "setp.lt.and.u32 ra, d, %21, ra;\n\t"
+        "sub.s32 d, %6, %10;\n\t"
+        "add.s32 d, d, -1;\n\t"
+        "setp.lt.and.u32 ra, d, %21, ra;\n\t"
+        "sub.s32 d, x, %11;\n\t"
+        "setp.lt.and.u32 rb, d, %21, rb;\n\t"
+        "sub.s32 d, %6, %12;\n\t"
+        "add.s32 d, d, -1;\n\t"
+        "setp.lt.and.u32 rb, d, %21, rb;\n\t"
+        /* p_concordant */
+        "sad.s32 o, %6, %5, 0;\n\t"
+        "sub.s32 k2, o, %22;\n\t"
+        "shr.u32 len, %23, 18;\n\t"
+        "and.b32 hb, %23, 0x3ffff;\n\t"
+        "min.u32 i1, o, len;\n\t"
+        "min.u32 i2, k2, len;\n\t"
+        "mad.lo.u32 a1, i1, 4, hb;\n\t"
+        "mad.lo.u32 a2, i2, 4, hb;\n\t"
+        "ld.shared.u32 h1, [a1];\n\t"
+        "ld.shared.u32 h2, [a2];\n\t"
+        "mul.lo.u32 l19, h1, 19;\n\t"
+        "setp.gt.u32 pc, l19, h2;\n\t"
+        "setp.eq.u32 pt, l19, h2;\n\t"
+        "setp.ne.and.u32 pt, h2, 0, pt;\n\t"
+        "setp.lt.s32 ptrap, %22, 0;\n\t"
+        "or.pred pt, pt, ptrap;\n\t"
+        "selp.s32 %4, 1, 0, pt;\n\t"
+        /* weights */
+        "setp.ne.s32 pdel, %14, 0;\n\t"
+        "and.pred both, ra, rb;\n\t"
+        "or.pred any, ra, rb;\n\t"
+        "and.pred x1, both, !pdel;\n\t"
+        "and.pred ron, any, !x1;\n\t"
+        "and.pred ron, ron, pc;\n\t"
+        "and.pred x1, pdel, pc;\n\t"
+        "and.pred aon, pa, !x1;\n\t"
+        "selp.b32 t, 0x3FF00000, 0x3FE00000, both;\n\t"
+        "selp.b32 t, t, 0, ron;\n\t"
+        "mov.b64 %2, {zr, t};\n\t"
+        "selp.b32 t, 0x3FF00000, 0, aon;\n\t"
+        "mov.b64 %3, {zr, t};\n\t"
+        "}"
+        : "=d"(hA), "=d"(hB), "=d"(wref), "=d"(walt), "=r"(tie)
+        : "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w),                                                 /* %5..%8   */
+          "r"(f0.x), "r"(f0.y), "r"(f0.z), "r"(f0.w), "r"(f1.x), "r"(f1.y), "r"(f1.w),            /* %9..%15  */
+          "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w), /* %16..%23 */
+          "r"(f2.x), "r"(f2.y), "r"(f2.z)                                                         /* %24..%26 */);
+}
+
+/* is_ref_seq of an EXTRA row's one interval [r.x, r.y) for the slot it names (rare path only) */
+__device__ __forceinline__ void extra_hits(const int4 r, const CSiteF &F, bool &hitA, bool &hitB)
+{
+    const unsigned w2 = (unsigned)r.z, w3 = (unsigned)r.w;
+    const bool slotB = (w3 & CF_MULTI_B) != 0;
+    const bool onA = slotB ? (w2 & CLS_B_ON_A) != 0 : (w2 & CLS_A_ON_A) != 0;
+    const bool onB = slotB ? (w2 & CLS_B_ON_B) != 0 : (w2 & CLS_A_ON_B) != 0;
+    const bool h = (onA && r.x <= F.wA0 && r.y >= F.wA1) || (onB && r.x <= F.wB0 && r.y >= F.wB1);
+    hitA = h && !slotB; hitB = h && slotB;
+}
+
+/* one 32-row fragment chunk of a FAST site (phase A); rows beyond the site's last one are zero */
+template <int ASSOC>
+__device__ __forceinline__ FragOut score_cfrag_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const CSiteF &F,
+                                                     const WinF *wf, const double *s_pm, const LibK *s_lib, const int lane,
+                                                     const int n, const int g, const int m, const int4 r,
+                                                     unsigned &carryA, unsigned &carryB, int &err)
+{
+    const unsigned full = 0xffffffffu;
+    const int4 f0 = *reinterpret_cast<const int4 *>(&F.wA0);
+    const int4 f1 = *reinterpret_cast<const int4 *>(&F.pat);
+    const unsigned z = (unsigned)r.w;
+    const unsigned lib = min((z >> 16) & kLibMaskC, (unsigned)kWLibs);
+    const uint4 w0 = *reinterpret_cast<const uint4 *>(&wf[lib].altA_lo);
+    const uint4 w1 = *reinterpret_cast<const uint4 *>(&wf[lib].FL);
+    const char *pmb = reinterpret_cast<const char *>(s_pm);
+    const double pmA = *reinterpret_cast<const double *>(pmb + ((z << 3) & 0x7F8u));
+    const double pmB = *reinterpret_cast<const double *>(pmb + ((z >> 5) & 0x7F8u));
+
+    double hA, hB, wref, walt;                      /* {0,1}, {0,1}, {0,.5,1}, {0,1} */
+    int tie;
+    if (f1.z == 1) crow_fast(r, f0, f1, w0, w1, hA, hB, wref, walt, tie);
+    else crow_gen(r, f0, f1, *reinterpret_cast<const int4 *>(&F.sgnA), w0, w1, hA, hB, wref, walt, tie);
+
+    /* one vote for everything rare: EXTRA / MULTI / CONT rows, a p_concordant tie or a library the integer
+     * rewrites do not cover; carried EXTRA hits re-enter through the carry bits */
+    unsigned vm = 0u, nm = 0u;
+    bool special = false;
+    const bool xrow = (z & (CF_EXTRA | CF_MULTI_A | CF_MULTI_B | CF_CONT)) != 0u;
+    if (__any_sync(full, xrow || tie != 0) || (carryA | carryB) != 0u) {
+        if (__any_sync(full, (z & (CF_EXTRA | CF_MULTI_A | CF_MULTI_B)) != 0u) || (((carryA | carryB) >> g) & 1u)) {
+            int fl = ((z & CF_CONT) ? F_CONT : 0) | ((z & CF_EXTRA) ? F_EXTRA : 0);
+            if (z & CF_EXTRA) {
+                bool xa, xb;
+                extra_hits(r, F, xa, xb);
+                hA = xa ? 1.0 : 0.0; hB = xb ? 1.0 : 0.0;
+            } else {
+                fl |= ((z & CF_MULTI_A) ? F_MULTI_A : 0) | ((z & CF_MULTI_B) ? F_MULTI_B : 0);
+            }
+            const MultiOut q = resolve_multi(fl, lane, n, g, (unsigned)__double2hiint(hA), (unsigned)__double2hiint(hB),
+                                             carryA, carryB);
+            hA = __hiloint2double((int)q.hAhi, 0); hB = __hiloint2double((int)q.hBhi, 0);
+            carryA = q.carryA; carryB = q.carryB; nm = q.nm; vm = q.vm;
+            special = nm != vm;
+        } else if (__any_sync(full, xrow)) {            /* CONT rows only */
+            vm = n >= 32 ? full : ((1u << n) - 1u);
+            nm = __ballot_sync(full, lane < n && !(z & CF_CONT));
+            special = nm != vm;
+        }
+        if (tie != 0 && (z & (CF_PAIRED | CF_EXTRA)) == CF_PAIRED) {       /* the literal row */
+            int4 lo, hi;
+            decode_wide(r, S.tB, lo, hi);
+            bool alt, refA, refB, pc;
+            slow_row(p, t, S, lo, hi, s_lib, m, err, alt, refA, refB, pc);
+            const bool is_del = F.del != 0;
+            const bool both = refA & refB;
+            const bool ref_on = (refA | refB) & (!both | is_del) & pc;
+            const bool alt_on = alt & !(is_del & pc);
+            wref = ref_on ? (both ? 1.0 : 0.5) : 0.0;
+            walt = alt_on ? 1.0 : 0.0;
+        }
+    }
+
+    const double prod = __dmul_rn(pmA, pmB);
+    const double vb = __dmul_rn(pmB, hB);
+    FragOut o;
+    o.s = __fma_rn(pmA, hA, vb);                       /* pmA * {0,1} is exact: one rounding, a + b */
+    o.p_ref = __dmul_rn(prod, wref); o.p_alt = __dmul_rn(prod, walt);
+    o.ia = 0; o.ib = 0; o.lead = 0; o.need_idx = false;
+    if (ASSOC == SVGT_ASSOC_CLASSIC) {
+        o.ia = hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0;
+    } else if (special && ((vm & ~nm) & ~(nm << 1)) == 0u) {
+        const unsigned NN = vm & ~nm;
+        const bool cont = (NN >> lane) & 1u, has_next = (NN >> 1 >> lane) & 1u;
+        const double us = __shfl_up_sync(full, o.s, 1), ur = __shfl_up_sync(full, o.p_ref, 1);
+        const double ua = __shfl_up_sync(full, o.p_alt, 1);
+        if (cont) {
+            o.s = __dadd_rn(__dadd_rn(us, __dmul_rn(pmA, hA)), vb);
+            o.p_ref = __dadd_rn(ur, o.p_ref); o.p_alt = __dadd_rn(ua, o.p_alt);
+        }
+        if (has_next) { o.s = 0.0; o.p_ref = 0.0; o.p_alt = 0.0; }
+    } else if (special) {
+        const FoldOut q = fold_continuations(lane, n, nm, vm, __dmul_rn(pmA, hA), vb, o.s, o.p_ref, o.p_alt);
+        o.s = q.s; o.p_ref = q.p_ref; o.p_alt = q.p_alt; o.lead = q.lead;
+        if (lane < q.lead) { o.ia = hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0; }
+    }
+    return o;
+}
+
+/* ---- split rows (parsers.py:1122-1215, singlesample.py:262-274), pre-digested per site ---- */
+struct CSplitF {
+    int loL, loR, w1, kind;          /* lo = pos - slop of the left / right breakend; w1 = 2 * slop + 1;
+                                        kind of a SOFT-CLIPPED row: 0 as a plain one (DEL), 1 DUP, 2 INV, 3 none */
+    unsigned mLL, mLR, mRL, mRR;     /* class bit: left piece on the left / right breakend's contig, right piece .. */
+    int rL, rR, pad0, pad1;
+};
+
+__device__ __forceinline__ CSplitF make_csplitf(const SiteS &S, int slop)
+{
+    CSplitF f;
+    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1, svtype = S.meta & 3;
+    const bool swap = (S.tA != S.tB) || (S.posA > S.posB);      /* parsers.py:1143-1161 */
+    f.loL = (swap ? S.posB : S.posA) - slop; f.loR = (swap ? S.posA : S.posB) - slop;
+    f.w1 = 2 * slop + 1;
+    f.rL = swap ? o2 : o1; f.rR = swap ? o1 : o2;
+    f.kind = svtype == SV_DEL ? 0 : svtype == SV_DUP ? 1 : svtype == SV_INV ? 2 : 3;
+    f.mLL = swap ? (1u << 29) : (1u << 28); f.mLR = swap ? (1u << 28) : (1u << 29);
+    f.mRL = swap ? (1u << 31) : (1u << 30); f.mRR = swap ? (1u << 30) : (1u << 31);
+    f.pad0 = 0; f.pad1 = 0;
+    return f;
+}
+
+template <int ASSOC>
+__device__ __forceinline__ SplitOut score_csplit_chunk(const CSplitF &F, const double *s_pm, const int lane, const int n,
+                                                       const int4 r)
+{
+    const unsigned full = 0xffffffffu;
+    const int4 f0 = *reinterpret_cast<const int4 *>(&F.loL);
+    const uint4 f1 = *reinterpret_cast<const uint4 *>(&F.mLL);
+    const int2 f2 = *reinterpret_cast<const int2 *>(&F.rL);
+    const unsigned z = (unsigned)r.w;
+    const bool soft = (z & CSP_SOFT) != 0u;
+    const bool first = (z & CSP_FIRST) != 0u;
+    int l_end = r.x + (int)((unsigned)r.z & 0xFFFFu), r_end = r.y + (int)((unsigned)r.z >> 16);
+    if (__any_sync(full, (z & CSP_WIDE) != 0u)) {          /* true ends ride in the next (XEND) row */
+        const int xe = __shfl_down_sync(full, r.x, 1), ye = __shfl_down_sync(full, r.y, 1);
+        if (z & CSP_WIDE) { l_end = xe; r_end = ye; }
+    }
+    const unsigned w1 = (unsigned)f0.z;
+    const int cl = f2.x ? r.x : l_end, cr = f2.y ? r.x : l_end;       /* left piece vs L / R side */
+    const int dl = f2.x ? r.y : r_end, dr = f2.y ? r.y : r_end;       /* right piece vs L / R side */
+    const bool lL = ((z & f1.x) != 0u) & ((unsigned)(cl - f0.x) < w1);
+    const bool lR = ((z & f1.y) != 0u) & ((unsigned)(cr - f0.y) < w1);
+    const bool rLs = ((z & f1.z) != 0u) & ((unsigned)(dl - f0.x) < w1);
+    const bool rRs = ((z & f1.w) != 0u) & ((unsigned)(dr - f0.y) < w1);
+    const int kind = soft ? f0.w : 0;
+    const bool Ls = kind == 0 ? lL : kind == 1 ? lR : kind == 2 ? (lL | lR) : false;
+    const bool Rs = kind == 0 ? rRs : kind == 1 ? rLs : kind == 2 ? (rLs | rRs) : false;
+    const double x = s_pm[Ls ? (z & 0xFFu) : 0u];
+    const double y = s_pm[Rs ? ((z >> 8) & 0xFFu) : 0u];
+    const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);       /* (.. + ..) / 2.0, exact either way */
+    SplitOut o;
+    o.vseq = soft ? 0.0 : p_alt; o.vclip = soft ? p_alt : 0.0; o.lead = 0;
+    const bool rv = lane < n;
+    if (ASSOC == SVGT_ASSOC_SSO && __any_sync(full, rv && !first)) {     /* extra splits of one fragment */
+        const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
+        const unsigned nm = __ballot_sync(full, rv && first);
+        const unsigned NN = vm & ~nm;
+        if ((NN & ~(nm << 1)) == 0u) {
+            const bool cont = (NN >> lane) & 1u, has_next = (NN >> 1 >> lane) & 1u;
+            const double us = __shfl_up_sync(full, o.vseq, 1), uc = __shfl_up_sync(full, o.vclip, 1);
+            if (cont) { o.vseq = __dadd_rn(us, o.vseq); o.vclip = __dadd_rn(uc, o.vclip); }
+            if (has_next) { o.vseq = 0.0; o.vclip = 0.0; }
+        } else {
+            const FoldOut q = fold_splits(lane, n, nm, o.vseq, o.vclip);
+            o.vseq = q.p_ref; o.vclip = q.p_alt; o.lead = q.lead;
+        }
+    }
+    return o;
+}
+
+}  // namespace

@@ -50,6 +50,18 @@ struct SvgtParams {
     int hist_in_smem;
 };
 
+/* compact-schema launch (svgt_compact.cu): `base` carries the tables, sizes, `out` (local rows: the sums are
+ * parked there between the two launches) and `status`; its sites / frags / splits are unused */
+struct SvgtCompactParams {
+    SvgtParams base;
+    const int4 *sites;              /* [n_sites][3]  48-byte site rows          */
+    const int4 *rows; long long n_rows;   /* [n_rows]  16-byte evidence rows    */
+    svgt_out_row_t *out_final;      /* where the call kernel writes the final rows (NULL: base.out) */
+    int *done_flag; int done_value; /* optional: set to done_value (system scope) once every final row is written */
+    unsigned hist_max;              /* largest histogram count, 0 = unknown     */
+    int ramp;
+};
+
 /* Returns a cudaError_t as int.  `grid` <= 0 lets the launcher size a persistent grid. */
 int svgt_launch_score(const SvgtParams &p, int variant, cudaStream_t stream);
 size_t svgt_score_smem_bytes(const SvgtParams &p, int variant);
@@ -58,3 +70,4 @@ int svgt_launch_call(const SvgtParams &p, cudaStream_t stream);
 int svgt_launch_ring(const SvgtParams &p, cudaStream_t stream);
 int svgt_launch_lean(const SvgtParams &p, int variant, cudaStream_t stream);
 int svgt_lean_launches(void);
+int svgt_launch_compact(const SvgtCompactParams &cp, int unit_mode, cudaStream_t stream);

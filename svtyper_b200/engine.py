@@ -19,6 +19,7 @@ import ctypes
 
 import numpy as np
 
+from . import compact as cp
 from . import evidence as ev
 from . import native
 
@@ -43,7 +44,8 @@ class DeviceBatch(object):
 
     def __init__(self, tensors, desc, n_sites, algorithmic_bytes):
         self.tensors = tensors          # keeps the device memory alive
-        self.desc = desc                # native.SvgtBatch with device pointers
+        self.desc = desc                # native.SvgtBatch / native.SvgtCBatch with device pointers
+        self.compact = isinstance(desc, native.SvgtCBatch)
         self.n_sites = n_sites
         self.algorithmic_bytes = algorithmic_bytes
         self.out = None
@@ -64,14 +66,34 @@ def _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_w
     return d
 
 
+def _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode,
+                 unit_mode=0, flags=0):
+    d = native.SvgtCBatch()
+    d.sites, d.n_sites = ptr["sites"], batch.n_sites
+    d.rows, d.n_rows = ptr["rows"], batch.n_rows
+    d.order = ptr.get("order")
+    d.lib_f64, d.lib_i32, d.n_lib = ptr["lib_f64"], ptr["lib_i32"], batch.libs.n_lib
+    d.hist, d.n_hist = ptr["hist"], int(batch.libs.hist.size)
+    d.hist_max = int(batch.libs.hist.max()) if batch.libs.hist.size else 1
+    d.pm, d.logt, d.n_log, d.consts = ptr["pm"], ptr["logt"], int(n_log), ptr["consts"]
+    d.min_aligned, d.split_slop, d.assoc_mode = int(min_aligned), int(split_slop), int(assoc_mode)
+    d.unit_mode = int(unit_mode)
+    d.split_weight, d.disc_weight = float(split_weight), float(disc_weight)
+    d.flags = int(flags)
+    return d
+
+
 def host_arrays(batch, split_weight=1.0, disc_weight=1.0):
-    """name -> contiguous numpy array for every field of svgt_batch_t."""
+    """name -> contiguous numpy array for every array field of svgt_batch_t / svgt_cbatch_t."""
     pm, logt, consts = luts_for(batch.log_table_size(split_weight, disc_weight))
-    arrs = {
-        "sites": batch.sites, "frags": batch.frags, "splits": batch.splits,
+    if isinstance(batch, cp.CompactBatch):
+        arrs = {"sites": batch.sites, "rows": batch.rows}
+    else:
+        arrs = {"sites": batch.sites, "frags": batch.frags, "splits": batch.splits}
+    arrs.update({
         "lib_f64": batch.libs.lib_f64, "lib_i32": batch.libs.lib_i32, "hist": batch.libs.hist,
         "pm": pm, "logt": logt, "consts": consts,
-    }
+    })
     if batch.order is not None:
         arrs["order"] = batch.order
     return {k: np.ascontiguousarray(v) for k, v in arrs.items()}
@@ -105,31 +127,43 @@ class Engine(object):
 
     # ---------------------------------------------------------------- host buffers in/out
     def score_host(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
-                   assoc_mode=ev.ASSOC_SSO, arrays=None, out=None):
-        """Score a host EvidenceBatch; returns OUT_DTYPE rows (numpy).
+                   assoc_mode=ev.ASSOC_SSO, arrays=None, out=None, site_order=True, unit_mode=0):
+        """Score a host batch (CompactBatch: the default path; EvidenceBatch: wide rows, the
+        compatibility entry); returns OUT_DTYPE rows (numpy).
 
         `arrays` may carry pre-built (e.g. pinned) host arrays from `host_arrays()`;
         `out` a pre-allocated (e.g. pinned) uint8/OUT_DTYPE buffer of n_sites rows.
+        `site_order`: the compact rows are laid out in site order (true for every packer and
+        converter of this package), which lets large batches be pipelined in site slices.
         """
         arrs = arrays if arrays is not None else host_arrays(batch, split_weight, disc_weight)
         ptr = {k: (v.data_ptr() if hasattr(v, "data_ptr") else v.ctypes.data) for k, v in arrs.items()}
         n_log = arrs["logt"].numel() if hasattr(arrs["logt"], "numel") else arrs["logt"].size
-        desc = _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode)
         if out is None:
             out = np.zeros(batch.n_sites, dtype=ev.OUT_DTYPE)
         optr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
-        rc = self._lib.svgt_ctx_score_host(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
+        if isinstance(batch, cp.CompactBatch):
+            desc = _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode,
+                                unit_mode, native.LAYOUT_SITE_ORDER if site_order else 0)
+            rc = self._lib.svgt_ctx_score_host_compact(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
+            launches = 2 if batch.n_sites else 0
+        else:
+            desc = _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode)
+            rc = self._lib.svgt_ctx_score_host(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
+            launches = self._lib.svgt_launches_per_batch(ctypes.byref(desc))
         h2d, d2h, ms = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_float()
         self._lib.svgt_ctx_last_traffic(self._ctx, ctypes.byref(h2d), ctypes.byref(d2h))
         self._lib.svgt_ctx_last_kernel_ms(self._ctx, ctypes.byref(ms))
         self.last_h2d, self.last_d2h, self.last_kernel_ms = h2d.value, d2h.value, ms.value
-        self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(desc))
+        if isinstance(batch, cp.CompactBatch) and h2d.value and batch.n_sites >= 131072 and site_order:
+            launches *= 8               # pipelined: one launch pair per site slice
+        self.launches += launches
         native.check(rc)
         return out
 
     # ---------------------------------------------------------------- device resident
     def upload(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
-               assoc_mode=ev.ASSOC_SSO):
+               assoc_mode=ev.ASSOC_SSO, unit_mode=0):
         torch = _torch()
         arrs = host_arrays(batch, split_weight, disc_weight)
         tens = {}
@@ -139,8 +173,12 @@ class Engine(object):
             t = torch.from_numpy(a) if a.size else torch.zeros(4, dtype=torch.from_numpy(a).dtype)
             tens[k] = t.to(self.device)
         ptr = {k: t.data_ptr() for k, t in tens.items()}
-        desc = _descriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
-                           disc_weight, assoc_mode)
+        if isinstance(batch, cp.CompactBatch):
+            desc = _cdescriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
+                                disc_weight, assoc_mode, unit_mode, native.LAYOUT_SITE_ORDER)
+        else:
+            desc = _descriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
+                               disc_weight, assoc_mode)
         dev = DeviceBatch(tens, desc, batch.n_sites, batch.algorithmic_bytes())
         dev.out = torch.zeros((max(batch.n_sites, 1), ev.OUT_BYTES), dtype=torch.uint8, device=self.device)
         dev.status = torch.zeros(4, dtype=torch.int32, device=self.device)
@@ -155,12 +193,15 @@ class Engine(object):
         torch = _torch()
         s = torch.cuda.current_stream(self.device) if stream is None else stream
         out = dev.out if out is None else out
+        fn = self._lib.svgt_score_compact if dev.compact else self._lib.svgt_score_batch
         with torch.cuda.device(self.device):
-            rc = self._lib.svgt_score_batch(ctypes.byref(dev.desc), ctypes.c_void_p(out.data_ptr()),
-                                            ctypes.c_void_p(dev.status.data_ptr()),
-                                            ctypes.c_void_p(s.cuda_stream))
+            rc = fn(ctypes.byref(dev.desc), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(dev.status.data_ptr()),
+                    ctypes.c_void_p(s.cuda_stream))
         native.check(rc)
-        self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(dev.desc))
+        if dev.compact:
+            self.launches += 2 if dev.n_sites else 0
+        else:
+            self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(dev.desc))
         return out
 
     def check(self, dev):

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVGT_LIB") or os.path.join(HERE, "libsvgt.so")   # SVGT_LIB: A/B builds of the same ABI
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_ARG, ERR_CUDA, ERR_LOG_TABLE, ERR_LIB_INDEX, ERR_NO_DEVICE, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6
 ERR_NAMES = {ERR_ARG: "SVGT_ERR_ARG", ERR_CUDA: "SVGT_ERR_CUDA", ERR_LOG_TABLE: "SVGT_ERR_LOG_TABLE",
              ERR_LIB_INDEX: "SVGT_ERR_LIB_INDEX", ERR_NO_DEVICE: "SVGT_ERR_NO_DEVICE",
@@ -23,7 +23,10 @@ VARIANTS = (0, 1, 2, 3, 4, 5, 6, 7)
 # every symbol include/svgt.h declares (tests check the library exports all of them)
 SYMBOLS = ("svgt_abi_version", "svgt_last_error", "svgt_device_count", "svgt_score_batch",
            "svgt_launches_per_batch", "svgt_set_variant", "svgt_ctx_create", "svgt_ctx_destroy",
-           "svgt_ctx_score_host", "svgt_ctx_last_traffic", "svgt_ctx_last_kernel_ms")
+           "svgt_ctx_score_host", "svgt_ctx_last_traffic", "svgt_ctx_last_kernel_ms",
+           "svgt_score_compact", "svgt_ctx_score_host_compact", "svgt_shared_alloc", "svgt_shared_open",
+           "svgt_shared_close", "svgt_shared_free", "svgt_wait_flags")
+LAYOUT_SITE_ORDER = 1
 
 
 class SvgtBatch(ctypes.Structure):
@@ -41,6 +44,26 @@ class SvgtBatch(ctypes.Structure):
         ("min_aligned", ctypes.c_int32), ("split_slop", ctypes.c_int32),
         ("assoc_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("split_weight", ctypes.c_double), ("disc_weight", ctypes.c_double),
+    ]
+
+
+class SvgtCBatch(ctypes.Structure):
+    """struct svgt_cbatch (include/svgt.h): the compact schema."""
+    _fields_ = [
+        ("sites", ctypes.c_void_p), ("n_sites", ctypes.c_int64),
+        ("rows", ctypes.c_void_p), ("n_rows", ctypes.c_int64),
+        ("order", ctypes.c_void_p),
+        ("lib_f64", ctypes.c_void_p), ("lib_i32", ctypes.c_void_p), ("n_lib", ctypes.c_int32),
+        ("hist_max", ctypes.c_uint32),
+        ("hist", ctypes.c_void_p), ("n_hist", ctypes.c_int64),
+        ("pm", ctypes.c_void_p),
+        ("logt", ctypes.c_void_p), ("n_log", ctypes.c_int64),
+        ("consts", ctypes.c_void_p),
+        ("min_aligned", ctypes.c_int32), ("split_slop", ctypes.c_int32),
+        ("assoc_mode", ctypes.c_int32), ("unit_mode", ctypes.c_int32),
+        ("split_weight", ctypes.c_double), ("disc_weight", ctypes.c_double),
+        ("out_final", ctypes.c_void_p), ("done_flag", ctypes.c_void_p),
+        ("done_value", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]
 
 
@@ -82,6 +105,20 @@ def lib():
                                             ctypes.POINTER(ctypes.c_int64)]
         L.svgt_ctx_last_kernel_ms.restype = ctypes.c_int
         L.svgt_ctx_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        L.svgt_score_compact.restype = ctypes.c_int
+        L.svgt_score_compact.argtypes = [ctypes.POINTER(SvgtCBatch), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.svgt_ctx_score_host_compact.restype = ctypes.c_int
+        L.svgt_ctx_score_host_compact.argtypes = [ctypes.c_void_p, ctypes.POINTER(SvgtCBatch), ctypes.c_void_p]
+        L.svgt_shared_alloc.restype = ctypes.c_int
+        L.svgt_shared_alloc.argtypes = [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]
+        L.svgt_shared_open.restype = ctypes.c_int
+        L.svgt_shared_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.svgt_shared_close.restype = ctypes.c_int
+        L.svgt_shared_close.argtypes = [ctypes.c_void_p]
+        L.svgt_shared_free.restype = ctypes.c_int
+        L.svgt_shared_free.argtypes = [ctypes.c_void_p]
+        L.svgt_wait_flags.restype = ctypes.c_int
+        L.svgt_wait_flags.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
         if L.svgt_abi_version() != ABI_VERSION:
             raise ImportError("libsvgt.so ABI %d != expected %d" % (L.svgt_abi_version(), ABI_VERSION))
         _lib = L
