@@ -116,6 +116,9 @@ typedef struct svgt_cbatch {
                                                  last final row is written (may be peer-mapped)           */
     int32_t done_value;
     int32_t flags;                            /* SVGT_LAYOUT_*                           */
+    int32_t rows_min_aligned;                 /* the -m the packer evaluated the MULTI rows' is_ref_seq bits
+                                                 with; must equal min_aligned (SVGT_ERR_ARG otherwise)     */
+    int32_t reserved;
 } svgt_cbatch_t;
 
 int svgt_abi_version(void);

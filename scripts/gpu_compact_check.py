@@ -30,8 +30,13 @@ def main():
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--config", default="del1m4lib")
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--cache", default="", help="directory holding / receiving the generated batch as .npy files")
+    ap.add_argument("--no-wide", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tag", default="")
     args = ap.parse_args()
     import torch
+    os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     eng = engine.Engine(0)
     fails = 0
     if not args.skip_parity:
@@ -81,13 +86,27 @@ def main():
 
     # ---- timing
     t0 = time.time()
-    wide = synth.generate_parallel(args.config, n_sites=args.sites)
-    cb = cp.compact_from_wide(wide)
-    print("gen %.1fs: sites %d wide rows %d+%d compact rows %d; alg bytes wide %.3f GB compact %.3f GB survey %.3f GB" % (
-        time.time() - t0, cb.n_sites, wide.n_frag, wide.n_split, cb.n_rows, wide.algorithmic_bytes() / 1e9,
-        cb.algorithmic_bytes() / 1e9, cb.survey_bytes() / 1e9), flush=True)
-    res = {}
-    for label, batch in (("compact", cb), ("wide-lean", wide)):
+    cdir = args.cache and os.path.join(args.cache, "%s_%d" % (args.config, args.sites))
+    wide = None
+    if cdir and os.path.exists(os.path.join(cdir, "rows.npy")):
+        libs = synth.make_libraries(synth.CONFIGS[args.config]["n_lib"])
+        cb = cp.CompactBatch(np.load(os.path.join(cdir, "sites.npy")), np.load(os.path.join(cdir, "rows.npy")), libs,
+                             np.load(os.path.join(cdir, "order.npy")))
+    else:
+        wide = synth.generate_parallel(args.config, n_sites=args.sites)
+        cb = cp.compact_from_wide(wide)
+        if cdir:
+            os.makedirs(cdir, exist_ok=True)
+            np.save(os.path.join(cdir, "sites.npy"), cb.sites)
+            np.save(os.path.join(cdir, "rows.npy"), cb.rows)
+            np.save(os.path.join(cdir, "order.npy"), cb.order)
+        if args.no_wide:
+            wide = None
+    print("gen %.1fs: sites %d compact rows %d (%d frag + %d split); alg bytes compact %.3f GB survey %.3f GB" % (
+        time.time() - t0, cb.n_sites, cb.n_rows, cb.n_frag, cb.n_split, cb.algorithmic_bytes() / 1e9, cb.survey_bytes() / 1e9),
+        flush=True)
+    res = {"tag": args.tag, "lib": os.path.basename(native.LIB_PATH)}
+    for label, batch in ((("compact", cb),) + ((("wide-lean", wide),) if wide is not None else ())):
         dev = eng.upload(batch)
         for _ in range(3):
             eng.score(dev)
@@ -112,6 +131,13 @@ def main():
     res["compact"]["frac_own_B"] = cb.algorithmic_bytes() / k / 1e9 / 6545.9
     res["compact"]["frac_survey_B"] = cb.survey_bytes() / k / 1e9 / 6545.9
     res["compact"]["Msites_per_s"] = cb.n_sites / k / 1e6
+    import hashlib
+    res["rows_md5"] = hashlib.md5(keep.tobytes()).hexdigest()
+    if args.no_e2e:
+        print(json.dumps(res), flush=True)
+        with open(os.path.join(REPO, "gpurun_out", "compact_check_%s.json" % (args.tag or "x")), "w") as f:
+            json.dump(res, f)
+        return 1 if fails else 0
     # end to end through the host API (pinned)
     arrs = engine.host_arrays(cb)
     pin = {}
@@ -128,7 +154,7 @@ def main():
                   "same_rows": bool(out.numpy().reshape(-1).view(ev.OUT_DTYPE).tobytes() == keep.tobytes())}
     print(json.dumps(res), flush=True)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(REPO, "gpurun_out", "compact_check.json"), "w") as f:
+    with open(os.path.join(REPO, "gpurun_out", "compact_check_%s.json" % (args.tag or "base")), "w") as f:
         json.dump({"fails": fails, "res": res}, f)
     return 1 if fails else 0
 

@@ -22,12 +22,14 @@ packer, host->device copies, the tally kernel -- moves the SAME evidence in 16-b
                  two breakend contigs -- parsers.py:805,833-834 -- so the comparison result is
                  what the row carries)
       3 mapqA [0:8) | mapqB [8:16) | library [16:25) | flags [25:32)
-                 25 PAIRED (num_primary == 2)  26 REV_A  27 REV_B  28 CONT  29 EXTRA
+                 25 PAIRED (num_primary == 2)  26 REV_A  27 REV_B  28 CONT  29 (reserved)
                  30 MULTI_A  31 MULTI_B
       A read whose aligned blocks are not one gap-free run (D / N operations), or whose span
-      does not fit 14 bits, is MULTI: its is_ref_seq hit comes from the EXTRA rows in front of it.
-  EXTRA row     0 start 1 end of ONE gap-free interval, 2 class bits of the slot it belongs to,
-                3 library | EXTRA | (CONT) | MULTI_A or MULTI_B naming the slot
+      does not fit 14 bits, is MULTI: the packer evaluates SamFragment.is_ref_seq for it
+      (parsers.py:801-816: CIGAR-block overlap with either breakend window, which needs the
+      batch's min_aligned -- recorded in CompactBatch.min_aligned and checked at launch) and the
+      row carries the outcome in its length field (lenX = 1 hit, 0 no hit).  Single-block reads,
+      practically all of them, are tested on the device from a_start / b_end / lenX.
 
   split row     int32 [4]  (16 B)    SplitRead.query_left / query_right (parsers.py:1017-1028)
       0 l_start  1 r_start
@@ -57,7 +59,7 @@ LEN_MAX = (1 << LEN_BITS) - 1
 CLS_A_ON_A, CLS_A_ON_B, CLS_B_ON_A, CLS_B_ON_B = 1 << 28, 1 << 29, 1 << 30, 1 << 31
 LIB_SHIFT, LIB_BITS = 16, 9
 LIB_MAX = (1 << LIB_BITS) - 1
-CF_PAIRED, CF_REV_A, CF_REV_B, CF_CONT, CF_EXTRA, CF_MULTI_A, CF_MULTI_B = (1 << b for b in range(25, 32))
+CF_PAIRED, CF_REV_A, CF_REV_B, CF_CONT, CF_RESERVED, CF_MULTI_A, CF_MULTI_B = (1 << b for b in range(25, 32))
 
 SLEN_MAX = 0xFFFF
 CSP_SOFT, CSP_FIRST, CSP_WIDE, CSP_XEND = 1 << 16, 1 << 17, 1 << 18, 1 << 19
@@ -68,11 +70,12 @@ FAKE_NONE = -3        # wide_from_compact(): "some other contig"
 class CompactBatch(object):
     """Host-side (numpy) batch in the compact device layout."""
 
-    def __init__(self, sites, rows, libs, order=None):
+    def __init__(self, sites, rows, libs, order=None, min_aligned=20):
         self.sites = np.ascontiguousarray(sites, dtype=np.int32).reshape(-1, CSITE_WORDS)
         self.rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, CROW_WORDS)
         self.libs = libs
         self.order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        self.min_aligned = int(min_aligned)     # the MULTI rows' hit bits were evaluated with this -m
 
     @property
     def n_sites(self): return self.sites.shape[0]
@@ -116,26 +119,29 @@ class CompactBatch(object):
         """Contiguous site range [lo, hi) as an independent batch (multi-GPU shards, slices)."""
         s = self.sites[lo:hi].copy()
         if s.shape[0] == 0:
-            return CompactBatch(s, np.zeros((0, CROW_WORDS), np.int32), self.libs)
+            return CompactBatch(s, np.zeros((0, CROW_WORDS), np.int32), self.libs, min_aligned=self.min_aligned)
         off = np.ascontiguousarray(s[:, 8:10]).view(np.int64).ravel()
         r0 = int(off[0])
         r1 = int(off[-1]) + int(s[-1, 10]) + int(s[-1, 11])
         s[:, 8:10] = (off - r0).view(np.int32).reshape(-1, 2)
-        return CompactBatch(s, self.rows[r0:r1], self.libs)
+        return CompactBatch(s, self.rows[r0:r1], self.libs, min_aligned=self.min_aligned)
 
 
 def _u32(a):
     return (np.asarray(a, dtype=np.int64) & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
 
 
-def compact_from_wide(batch: ev.EvidenceBatch, alloc=None) -> CompactBatch:
+def compact_from_wide(batch: ev.EvidenceBatch, alloc=None, min_aligned=20) -> CompactBatch:
     """Re-encode a wide EvidenceBatch (evidence.py) as a CompactBatch.
 
     Vectorised; rows come out site by site (fragment rows, then split rows), so the result is
-    always laid out in site order whatever the wide batch's offsets were.
+    always laid out in site order whatever the wide batch's offsets were.  The wide layout's EXTRA
+    interval rows are consumed here: is_ref_seq of a gapped (MULTI) read is evaluated against the
+    two breakend windows (pos -/+ min_aligned, parsers.py:801-816) and travels as one bit.
     `alloc(name, shape, dtype)` may supply the destination arrays (e.g. pinned host memory).
     """
     alloc = alloc or (lambda name, shape, dtype: np.empty(shape, dtype=dtype))
+    m = int(min_aligned)
     S = batch.sites.astype(np.int64)
     n = S.shape[0]
     nf_w = S[:, 12].copy()
@@ -146,7 +152,6 @@ def compact_from_wide(batch: ev.EvidenceBatch, alloc=None) -> CompactBatch:
     nf_w[skip] = 0            # SKIP sites carry no rows the path may look at
     ns_w[skip] = 0
 
-    # ---- fragment rows, gathered in site order
     def gather_index(off, cnt):
         tot = int(cnt.sum())
         if tot == 0:
@@ -156,6 +161,7 @@ def compact_from_wide(batch: ev.EvidenceBatch, alloc=None) -> CompactBatch:
         idx = off[site_of] + (np.arange(tot, dtype=np.int64) - start[site_of])
         return idx, site_of
 
+    # ---- fragment rows, gathered in site order
     fidx, fsite = gather_index(foff, nf_w)
     F = batch.frags[fidx].astype(np.int64) if fidx.size else np.zeros((0, ev.FRAG_WORDS), np.int64)
     tA, tB = S[fsite, 6], S[fsite, 7]
@@ -170,57 +176,52 @@ def compact_from_wide(batch: ev.EvidenceBatch, alloc=None) -> CompactBatch:
     main = ~isx
     if fidx.size and not (hasA[main].all() and hasB[main & paired].all()):
         raise ValueError("wide fragment rows must hold read A, and read B when PAIRED")
-    clsA = np.where(F[:, 4] == tA, CLS_A_ON_A, 0) | np.where(F[:, 4] == tB, CLS_A_ON_B, 0)
-    clsB = np.where(F[:, 5] == tA, CLS_B_ON_A, 0) | np.where(F[:, 5] == tB, CLS_B_ON_B, 0)
+    onAA, onAB = F[:, 4] == tA, F[:, 4] == tB
+    onBA, onBB = F[:, 5] == tA, F[:, 5] == tB
+    clsA = np.where(onAA, CLS_A_ON_A, 0) | np.where(onAB, CLS_A_ON_B, 0)
+    clsB = np.where(onBA, CLS_B_ON_A, 0) | np.where(onBB, CLS_B_ON_B, 0)
     lenA = F[:, 1] - F[:, 0]
     lenB = F[:, 3] - F[:, 2]
+    # is_ref_seq of one gap-free interval [s, e) against both windows (the oracle's ref_seq_hit())
+    wA0, wA1 = S[fsite, 0] - m, S[fsite, 0] + m
+    wB0, wB1 = S[fsite, 1] - m, S[fsite, 1] + m
+
+    def interval_hit(on_a, on_b, s_, e_):
+        return (on_a & (wA0 >= 0) & (s_ <= wA0) & (e_ >= wA1)) | (on_b & (wB0 >= 0) & (s_ <= wB0) & (e_ >= wB1))
+
+    hitA_iv = hasA & interval_hit(onAA, onAB, F[:, 0], F[:, 1])
+    hitB_iv = hasB & interval_hit(onBA, onBB, F[:, 2], F[:, 3])
+    # EXTRA rows feed the next main row of their site: OR their hits into that row's group
+    NW = F.shape[0]
+    grp = np.cumsum(main) - main            # EXTRA rows share the id of the main row that follows them
+    n_main = int(main.sum())
+    pendA = np.zeros(n_main + 1, dtype=bool)
+    pendB = np.zeros(n_main + 1, dtype=bool)
+    if isx.any():
+        main_site = np.full(n_main + 1, -1, dtype=np.int64)
+        main_site[:n_main] = fsite[main]
+        ok = isx & (main_site[grp] == fsite)          # a trailing EXTRA run with no main row in its site feeds nothing
+        np.logical_or.at(pendA, grp[ok & hitA_iv], True)
+        np.logical_or.at(pendB, grp[ok & hitB_iv], True)
+    multiA = main & (((fl & ev.F_MULTI_A) != 0) | (lenA < 0) | (lenA > LEN_MAX))
+    multiB = main & hasB & (((fl & ev.F_MULTI_B) != 0) | (lenB < 0) | (lenB > LEN_MAX))
+    # a read flagged MULTI takes the EXTRA rows' verdict; one that is merely too long for the length field its own
+    hitA = np.where((fl & ev.F_MULTI_A) != 0, pendA[grp], hitA_iv)
+    hitB = np.where((fl & ev.F_MULTI_B) != 0, pendB[grp], hitB_iv)
     cflags = (np.where(paired, CF_PAIRED, 0) | np.where(fl & ev.F_REV_A, CF_REV_A, 0)
               | np.where(fl & ev.F_REV_B, CF_REV_B, 0) | np.where(fl & ev.F_CONT, CF_CONT, 0)
-              | np.where(fl & ev.F_MULTI_A, CF_MULTI_A, 0) | np.where(fl & ev.F_MULTI_B, CF_MULTI_B, 0))
-    # main rows whose span does not fit the length field: escape through an EXTRA row of their own
-    longA = main & ~((fl & ev.F_MULTI_A) != 0) & ((lenA < 0) | (lenA > LEN_MAX))
-    longB = main & hasB & ~((fl & ev.F_MULTI_B) != 0) & ((lenB < 0) | (lenB > LEN_MAX))
-    # output rows per wide row: EXTRA rows -> one per present slot; main rows -> 1 (+1 per escape)
-    n_out = np.where(isx, hasA.astype(np.int64) + hasB.astype(np.int64),
-                     1 + longA.astype(np.int64) + longB.astype(np.int64))
-    out_pos = np.cumsum(n_out) - n_out
-    NF = int(n_out.sum())
-    nf_c = np.bincount(fsite, weights=n_out, minlength=n).astype(np.int64) if fidx.size else np.zeros(n, np.int64)
-
+              | np.where(multiA, CF_MULTI_A, 0) | np.where(multiB, CF_MULTI_B, 0))
+    NF = n_main
+    nf_c = np.bincount(fsite[main], minlength=n).astype(np.int64) if NF else np.zeros(n, np.int64)
     R = np.zeros((NF, 4), dtype=np.int64)
     if NF:
-        libw = lib << LIB_SHIFT
-        # EXTRA rows, slot A then slot B
-        xa = isx & hasA
-        p = out_pos[xa]
-        R[p, 0], R[p, 1] = F[xa, 0], F[xa, 1]
-        R[p, 2] = clsA[xa]
-        R[p, 3] = libw[xa] | CF_EXTRA | CF_MULTI_A | np.where(fl[xa] & ev.F_CONT, CF_CONT, 0)
-        xb = isx & hasB
-        p = out_pos[xb] + hasA[xb]
-        R[p, 0], R[p, 1] = F[xb, 2], F[xb, 3]
-        R[p, 2] = clsB[xb]
-        R[p, 3] = libw[xb] | CF_EXTRA | CF_MULTI_B | np.where(fl[xb] & ev.F_CONT, CF_CONT, 0)
-        # escapes of over-long reads (in front of their main row)
-        p = out_pos[longA]
-        R[p, 0], R[p, 1] = F[longA, 0], F[longA, 1]
-        R[p, 2] = clsA[longA]
-        R[p, 3] = libw[longA] | CF_EXTRA | CF_MULTI_A | np.where(fl[longA] & ev.F_CONT, CF_CONT, 0)
-        p = out_pos[longB] + longA[longB]
-        R[p, 0], R[p, 1] = F[longB, 2], F[longB, 3]
-        R[p, 2] = clsB[longB]
-        R[p, 3] = libw[longB] | CF_EXTRA | CF_MULTI_B | np.where(fl[longB] & ev.F_CONT, CF_CONT, 0)
-        # main rows
-        mA = main & (((fl & ev.F_MULTI_A) != 0) | longA)
-        mB = main & (((fl & ev.F_MULTI_B) != 0) | longB)
-        la = np.where(mA, 0, lenA)
-        lb = np.where(mB | ~hasB, 0, lenB)
-        p = (out_pos + n_out - 1)[main]
-        R[p, 0] = F[main, 0]
-        R[p, 1] = np.where(hasB[main], F[main, 3], 0)
-        R[p, 2] = la[main] | (lb[main] << LEN_BITS) | clsA[main] | np.where(hasB[main], clsB[main], 0)
-        R[p, 3] = ((F[main, 6] & 0xFF) | np.where(hasB[main], F[main, 6] & 0xFF00, 0) | libw[main] | cflags[main]
-                   | np.where(mA[main], CF_MULTI_A, 0) | np.where(mB[main], CF_MULTI_B, 0))
+        la = np.where(multiA, hitA.astype(np.int64), lenA)[main]
+        lb = np.where(multiB, hitB.astype(np.int64), np.where(hasB, lenB, 0))[main]
+        hb = hasB[main]
+        R[:, 0] = F[main, 0]
+        R[:, 1] = np.where(hb, F[main, 3], 0)
+        R[:, 2] = la | (lb << LEN_BITS) | clsA[main] | np.where(hb, clsB[main], 0)
+        R[:, 3] = ((F[main, 6] & 0xFF) | np.where(hb, F[main, 6] & 0xFF00, 0) | (lib[main] << LIB_SHIFT) | cflags[main])
 
     # ---- split rows
     sidx, ssite = gather_index(soff, ns_w)
@@ -281,7 +282,7 @@ def compact_from_wide(batch: ev.EvidenceBatch, alloc=None) -> CompactBatch:
     cs[:, 10], cs[:, 11] = nf_c, ns_c
     sites[:] = _u32(cs)
     out = CompactBatch.__new__(CompactBatch)
-    out.sites, out.rows, out.libs, out.order = sites, rows, batch.libs, None
+    out.sites, out.rows, out.libs, out.order, out.min_aligned = sites, rows, batch.libs, None, m
     if batch.order is not None:
         order = alloc("order", (n,), np.int32)
         order[:] = out.length_order()
@@ -318,39 +319,63 @@ def wide_from_compact(cb: CompactBatch) -> ev.EvidenceBatch:
     def s32(a):
         return (a & 0xFFFFFFFF).astype(np.uint32).view(np.int32).astype(np.int64)
 
+    m = cb.min_aligned
     R, fs = rows_of(off, nf)
     w2, w3 = R[:, 2], R[:, 3]
-    isx = (w3 & CF_EXTRA) != 0
-    slotB = isx & ((w3 & CF_MULTI_B) != 0)
-    slotA = isx & ~slotB
     paired = (w3 & CF_PAIRED) != 0
-    F = np.zeros((R.shape[0], ev.FRAG_WORDS), dtype=np.int64)
     a_start, b_end = s32(R[:, 0]), s32(R[:, 1])
     lenA, lenB = w2 & LEN_MAX, (w2 >> LEN_BITS) & LEN_MAX
+    multiA, multiB = (w3 & CF_MULTI_A) != 0, (w3 & CF_MULTI_B) != 0
     # a second read that is not part of a pair shows only through its fields (one on neither
     # breakend contig with no span cannot contribute anything, so dropping it changes nothing)
-    hasB = paired | ((w2 & (CLS_B_ON_A | CLS_B_ON_B)) != 0) | (lenB != 0) | ((w3 & CF_MULTI_B) != 0) | (b_end != 0)
-    tA_read = tid_from((w2 & CLS_A_ON_A) != 0, (w2 & CLS_A_ON_B) != 0, fs)
-    tB_read = tid_from((w2 & CLS_B_ON_A) != 0, (w2 & CLS_B_ON_B) != 0, fs)
+    hasB = paired | ((w2 & (CLS_B_ON_A | CLS_B_ON_B)) != 0) | (lenB != 0) | multiB | (b_end != 0)
+    onAA, onAB = (w2 & CLS_A_ON_A) != 0, (w2 & CLS_A_ON_B) != 0
+    onBA, onBB = (w2 & CLS_B_ON_A) != 0, (w2 & CLS_B_ON_B) != 0
+    tA_read = tid_from(onAA, onAB, fs)
+    tB_read = tid_from(onBA, onBB, fs)
     lib = (w3 >> LIB_SHIFT) & LIB_MAX
-    main = ~isx
-    F[main, 0] = a_start[main]
-    F[main, 1] = (a_start + lenA)[main]
-    F[main, 2] = np.where(hasB, b_end - lenB, 0)[main]
-    F[main, 3] = np.where(hasB, b_end, 0)[main]
-    F[main, 4] = tA_read[main]
-    F[main, 5] = np.where(hasB, tB_read, 0)[main]
-    F[main, 6] = ((w3 & 0xFFFF) | (lib << 16))[main]
-    flags = (ev.F_HAS_A | np.where(hasB, ev.F_HAS_B, 0) | np.where(paired, ev.F_PAIRED, 0) | np.where(w3 & CF_REV_A, ev.F_REV_A, 0)
-             | np.where(w3 & CF_REV_B, ev.F_REV_B, 0) | np.where(w3 & CF_CONT, ev.F_CONT, 0)
-             | np.where(w3 & CF_MULTI_A, ev.F_MULTI_A, 0) | np.where(w3 & CF_MULTI_B, ev.F_MULTI_B, 0))
-    F[main, 7] = flags[main]
-    xfl = ev.F_EXTRA | np.where(w3 & CF_CONT, ev.F_CONT, 0)
-    F[slotA, 0], F[slotA, 1], F[slotA, 4] = a_start[slotA], b_end[slotA], tA_read[slotA]
-    F[slotA, 7] = (xfl | ev.F_HAS_A)[slotA]
-    F[slotB, 2], F[slotB, 3], F[slotB, 5] = a_start[slotB], b_end[slotB], tB_read[slotB]
-    F[slotB, 7] = (xfl | ev.F_HAS_B)[slotB]
-    F[isx, 6] = (lib << 16)[isx]
+    # a MULTI read with its hit bit set becomes MULTI + one EXTRA row whose interval is the window it covers
+    posA, posB = s32(S[fs, 0]), s32(S[fs, 1])
+    xA = multiA & (lenA != 0)
+    xB = multiB & (lenB != 0)
+    n_out = 1 + xA.astype(np.int64) + xB.astype(np.int64)
+    pos = np.cumsum(n_out) - n_out
+    NW = int(n_out.sum())
+    F = np.zeros((NW, ev.FRAG_WORDS), dtype=np.int64)
+
+    def window_of(on_a, on_b):
+        use_a = on_a & (posA - m >= 0)
+        use_b = ~use_a & on_b & (posB - m >= 0)
+        if not (use_a | use_b)[xsel].all():
+            raise ValueError("MULTI hit bit set on a read that can reach neither breakend window")
+        return np.where(use_a, posA, posB) - m, np.where(use_a, posA, posB) + m
+
+    for xsel, on_a, on_b, slot_b in ((xA, onAA, onAB, False), (xB, onBA, onBB, True)):
+        if not xsel.any():
+            continue
+        lo_, hi_ = window_of(on_a, on_b)
+        p = (pos + (xA & slot_b))[xsel]
+        cfl = np.where(w3 & CF_CONT, ev.F_CONT, 0)[xsel]
+        if slot_b:
+            F[p, 2], F[p, 3], F[p, 5] = lo_[xsel], hi_[xsel], tB_read[xsel]
+            F[p, 7] = ev.F_EXTRA | ev.F_HAS_B | cfl
+        else:
+            F[p, 0], F[p, 1], F[p, 4] = lo_[xsel], hi_[xsel], tA_read[xsel]
+            F[p, 7] = ev.F_EXTRA | ev.F_HAS_A | cfl
+        F[p, 6] = (lib << 16)[xsel]
+    pm_ = pos + n_out - 1
+    F[pm_, 0] = a_start
+    F[pm_, 1] = a_start + np.where(multiA, 0, lenA)
+    F[pm_, 2] = np.where(hasB, b_end - np.where(multiB, 0, lenB), 0)
+    F[pm_, 3] = np.where(hasB, b_end, 0)
+    F[pm_, 4] = tA_read
+    F[pm_, 5] = np.where(hasB, tB_read, 0)
+    F[pm_, 6] = (w3 & 0xFFFF) | (lib << 16)
+    F[pm_, 7] = (ev.F_HAS_A | np.where(hasB, ev.F_HAS_B, 0) | np.where(paired, ev.F_PAIRED, 0)
+                 | np.where(w3 & CF_REV_A, ev.F_REV_A, 0) | np.where(w3 & CF_REV_B, ev.F_REV_B, 0)
+                 | np.where(w3 & CF_CONT, ev.F_CONT, 0) | np.where(multiA, ev.F_MULTI_A, 0)
+                 | np.where(multiB, ev.F_MULTI_B, 0))
+    nf_wide = np.bincount(fs, weights=n_out, minlength=n).astype(np.int64) if R.shape[0] else np.zeros(n, np.int64)
 
     C, ss = rows_of(off + nf, ns)
     w2, w3 = C[:, 2], C[:, 3]
@@ -376,9 +401,9 @@ def wide_from_compact(cb: CompactBatch) -> ev.EvidenceBatch:
     sites[:, 6], sites[:, 7] = tidA, tidB
     sites[:, 8] = s32(S[:, 6])
     sites[:, 9] = S[:, 7] & 0x1F
-    f0 = np.cumsum(nf) - nf
+    f0 = np.cumsum(nf_wide) - nf_wide
     s0 = np.cumsum(ns) - ns
-    sites[:, 10], sites[:, 11], sites[:, 12] = f0 & 0xFFFFFFFF, f0 >> 32, nf
+    sites[:, 10], sites[:, 11], sites[:, 12] = f0 & 0xFFFFFFFF, f0 >> 32, nf_wide
     sites[:, 13], sites[:, 14], sites[:, 15] = s0 & 0xFFFFFFFF, s0 >> 32, ns
     return ev.EvidenceBatch(_u32(sites), _u32(F), _u32(Q), cb.libs,
                             None if cb.order is None else cb.order.copy())

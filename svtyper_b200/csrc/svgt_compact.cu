@@ -13,8 +13,9 @@
  *     summed byte count.  The warp polls that barrier once per super-step and each lane then reads its row
  *     with one conflict-free LDS.128.  No per-lane copy instructions, no registers or scoreboards held by
  *     rows in flight, a whole super-step (2-3 us of scoring) of prefetch distance;
- *   - phase A (score_cfrag_chunk / score_csplit_chunk): one row per lane, straight-line predicate chain,
- *     three doubles {a + b, p_ref, p_alt} parked structure-of-arrays in shared memory;
+ *   - phase A (score_cfrag_chunk / score_csplit_chunk): one row per lane, straight-line predicate chain;
+ *     the three doubles a row yields {a + b, p_ref, p_alt} are parked structure-of-arrays -- p_ref / p_alt
+ *     over the site's 512 bytes of the ring slot the rows were just read from, a + b beside it;
  *   - phase B after each super-step: lane 4g + c replays chain c of site g over the <= 32 parked rows in
  *     row order (the fp64 sums are order-sensitive: SURVEY.md H1), 3 G chains side by side;
  *   - the five sums of a site are parked in its 80-byte row of `out`; svgt_call_compact_kernel (one site
@@ -27,10 +28,13 @@
 namespace {
 
 #ifndef SVGT_C_THREADS
-#define SVGT_C_THREADS 448          /* 14 warps: 13.8 KB of per-warp state each + the per-CTA tables fill the 227 KB */
+#define SVGT_C_THREADS 480          /* 15 warps x 13.6 KB of per-warp state + the per-CTA tables fill the 227 KB */
 #endif
 #ifndef SVGT_C_G
 #define SVGT_C_G 8
+#endif
+#ifndef SVGT_C_MINB
+#define SVGT_C_MINB 1
 #endif
 #ifndef SVGT_C_DEPTH
 #define SVGT_C_DEPTH 2              /* super-step slots in the ring */
@@ -41,9 +45,8 @@ constexpr int kCHistPad = 8;
 
 template <int G>
 struct alignas(128) CWarpSmem {
-    int4 ring[kCD][G][33];          /* TMA destinations: [slot][site][row]; once a lane has read its row, the same 16
-                                       bytes park {p_ref, p_alt} (or {alt_seq, alt_clip}) for phase B.  33-row
-                                       stride: the chain lanes of different sites read distinct banks */
+    int4 ring[kCD][G][33];          /* TMA destinations: [slot][site][row].  Once the warp has read a site's rows, the
+                                       same 528 bytes park p_ref[33] | p_alt[33] (or alt_seq | alt_clip) for phase B */
     double spark[G][33];            /* parked a + b (or the two LUT indices where phase B needs a and b apart) */
     unsigned long long bar[kCD];    /* one mbarrier per slot */
     int cnt[2][8];                  /* [0] fragment rows, [1] split rows of each site (uniform reads) */
@@ -51,7 +54,6 @@ struct alignas(128) CWarpSmem {
     CSiteF sf[G];
     CSplitF spf[G];
     WinF wf[G][kWLibs + 1];
-    Win gwin[kWLibs];               /* windows of the non-fast site being scored */
     double zero[2];
 };
 
@@ -96,34 +98,13 @@ __host__ __device__ __forceinline__ long long c_n_units(long long n_sites, long 
 
 __device__ __forceinline__ unsigned c_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-/* non-fast sites (a breakend within min_aligned of the contig start): the wide-row cooperative scorer on
- * decoded rows, out of line */
-struct CGenericOut { FragOut fo; unsigned carryA, carryB; int err; };
-
+/* phase B of one fragment chunk for chain c: `px` = the chain's 33 parked doubles (c = 0: a + b, or the LUT
+ * index pairs `pi` where a and b must be added apart); the replay of replay_frag_soa() */
 template <int ASSOC>
-__device__ __noinline__ CGenericOut c_generic_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const Win *wins,
-                                                    const double *s_pm, const LibK *s_lib, const int lane, const int n,
-                                                    const int g, const int m, const int4 r, unsigned carryA,
-                                                    unsigned carryB, int err)
-{
-    int4 lo, hi;
-    decode_wide(r, S.tB, lo, hi);
-    if (lane >= n) { lo = make_int4(0, 0, 0, 0); hi = lo; }
-    CGenericOut q;
-    q.fo = score_frag_chunk<ASSOC>(p, t, S, wins, s_pm, s_lib, p.hist, lane, n, g, m, lo, hi, carryA, carryB, err);
-    q.carryA = carryA; q.carryB = carryB; q.err = err;
-    return q;
-}
-
-/* phase B of one fragment chunk for chain c (0 ref_seq: `s`, 8-byte stride; 1 ref_span / 2 alt_span: the two
- * halves of the 16-byte parked rows `pr`); same replay as replay_frag_soa() */
-template <int ASSOC>
-__device__ __forceinline__ void c_replay_frag(const double *s, const double *pr, int c, int cnt, int lead, const double *s_pm,
+__device__ __forceinline__ void c_replay_frag(const double *px, const double *s, int c, int cnt, int lead, const double *s_pm,
                                               double &acc, double &pend)
 {
     const int2 *pi = reinterpret_cast<const int2 *>(s);                 /* .x = ia, .y = ib */
-    const double *px = c == 0 ? s : pr + (c - 1);
-    const int st = c == 0 ? 1 : 2;
     if (cnt <= 0) return;
     lead = lead < cnt ? lead : cnt;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
@@ -134,7 +115,7 @@ __device__ __forceinline__ void c_replay_frag(const double *s, const double *pr,
             }
         } else {
 #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 2]);
+            for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j]);
         }
     } else {
         for (int j = 0; j < lead; ++j) {                /* rows continuing the previous chunk's last fragment */
@@ -142,39 +123,38 @@ __device__ __forceinline__ void c_replay_frag(const double *s, const double *pr,
                 const int2 ix = pi[j];
                 pend = __dadd_rn(__dadd_rn(pend, s_pm[ix.x]), s_pm[ix.y]);
             } else {
-                pend = __dadd_rn(pend, px[j * 2]);
+                pend = __dadd_rn(pend, px[j]);
             }
         }
 #pragma unroll 8
         for (int j = lead; j < cnt; ++j) {
             acc = __dadd_rn(acc, pend);
-            pend = px[j * st];
+            pend = px[j];
         }
     }
 }
 
-/* phase B of one split chunk for chain c (0 alt_seq, 1 alt_clip) */
+/* phase B of one split chunk for one chain (alt_seq or alt_clip) */
 template <int ASSOC>
-__device__ __forceinline__ void c_replay_split(const double *pr, int c, int cnt, int lead, double &acc, double &pend)
+__device__ __forceinline__ void c_replay_split(const double *px, int cnt, int lead, double &acc, double &pend)
 {
-    const double *px = pr + c;
     if (cnt <= 0) return;
     lead = lead < cnt ? lead : cnt;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
 #pragma unroll 4
-        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j * 2]);
+        for (int j = 0; j < cnt; ++j) acc = __dadd_rn(acc, px[j]);
     } else {
-        for (int j = 0; j < lead; ++j) pend = __dadd_rn(pend, px[j * 2]);
+        for (int j = 0; j < lead; ++j) pend = __dadd_rn(pend, px[j]);
 #pragma unroll 8
         for (int j = lead; j < cnt; ++j) {
             acc = __dadd_rn(acc, pend);
-            pend = px[j * 2];
+            pend = px[j];
         }
     }
 }
 
 template <int G, int ASSOC>
-__global__ void __launch_bounds__(SVGT_C_THREADS, 1) svgt_compact_kernel(const SvgtCompactParams cp)
+__global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kernel(const SvgtCompactParams cp)
 {
     typedef CWarpSmem<G> WS;
     const SvgtParams &p = cp.base;
@@ -299,18 +279,20 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, 1) svgt_compact_kernel(const S
                 F.wA0 = a.x - m; F.wA1 = a.x + m; F.wB0 = a.y - m; F.wB1 = a.y + m;
                 F.pat = (int)(CF_PAIRED | ((meta & SITE_O1_REV) ? CF_REV_A : 0u) | ((meta & SITE_O2_REV) ? CF_REV_B : 0u));
                 F.del = svtype == SV_DEL;
-                const bool okwin = (a.x - m >= 0) && (a.y - m >= 0);
-                F.fast = !okwin ? 0 : (svtype != SV_INV && same) ? 1 : 2;
+                const bool okA = a.x - m >= 0, okB = a.y - m >= 0;      /* max(0, pos - m) cuts the window short: never covered */
+                F.fast = (okA && okB && svtype != SV_INV && same) ? 1 : 2;
                 F.m21 = 2 * m - 1;
                 F.sgnA = (meta & SITE_O1_REV) ? 1 : -1; F.sgnB = (meta & SITE_O2_REV) ? 1 : -1;
                 F.inv = svtype == SV_INV; F.same = same;
+                F.mAA = okA ? CLS_A_ON_A : 0u; F.mAB = okB ? CLS_A_ON_B : 0u;
+                F.mBA = okA ? CLS_B_ON_A : 0u; F.mBB = okB ? CLS_B_ON_B : 0u;
                 ws.spf[lane] = make_csplitf(S, slop);
                 ws.cnt[0][lane] = nf; ws.cnt[1][lane] = ns;
             }
             __syncwarp();
             for (int i = lane; i < G * (kWLibs + 1); i += 32) {
                 const int g = i / (kWLibs + 1), l = i % (kWLibs + 1);
-                if (ws.site[g].nf && ws.sf[g].fast)
+                if (ws.site[g].nf)
                     ws.wf[g][l] = make_winf(ws.site[g], s_lib[l < nl ? l : 0], s_libf[l < nl ? l : kWLibs], m, zero_addr);
             }
             __syncwarp();
@@ -348,8 +330,7 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, 1) svgt_compact_kernel(const S
 
         double sum_frag = 0.0, sum_split = 0.0;
         double acc = 0.0, pend = 0.0;
-        unsigned carryA = 0u, carryB = 0u;
-        unsigned long long leads = 0ull;
+        unsigned long long leads = 0ull;            /* `lead` of each site's chunk in this super-step, 8 bits per site */
 #pragma unroll 1
         for (int k = 0; k < kCD - 1 && k < T; ++k) issue(k, (tt + (unsigned)k) % (unsigned)kCD);
 #pragma unroll 1
@@ -368,40 +349,30 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, 1) svgt_compact_kernel(const S
             const int step = sp ? k - nsf : k;
             const int *cnts = &ws.cnt[sp ? 1 : 0][0];
             const unsigned slotaddr = ring0 + slot * (unsigned)(G * 528);
-            const unsigned rowaddr = slotaddr + (unsigned)lane * 16u;
 #pragma unroll 1
             for (int g = 0; g < G; ++g) {
                 const int n = cnts[g] - step * 32;
                 if (n <= 0) continue;
+                const unsigned site_addr = slotaddr + (unsigned)g * 528u;
                 int4 r;
                 asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                             : "r"(rowaddr + (unsigned)g * 528u));
+                             : "r"(site_addr + (unsigned)lane * 16u));
                 if (lane >= n) r = make_int4(0, 0, 0, 0);   /* the copy stopped at the site's last row */
+                __syncwarp();                               /* every lane holds its row: the site's bytes are free to park in */
+                const unsigned pk = site_addr + (unsigned)lane * 8u;
                 if (!sp) {
-                    FragOut fo;
-                    if (ws.sf[g].fast) {
-                        fo = score_cfrag_chunk<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, n, g, m, r,
-                                                      carryA, carryB, err);
-                    } else {
-                        __syncwarp();
-                        if (lane < kWLibs) {
-                            if (lane < nl) ws.gwin[lane] = make_win(ws.site[g], s_lib[lane], m, small_counts);
-                            else ws.gwin[lane].flags = 0u;
-                        }
-                        __syncwarp();
-                        const CGenericOut q = c_generic_chunk<ASSOC>(p, t, ws.site[g], &ws.gwin[0], s_pm, s_lib, lane, n, g, m,
-                                                                     r, carryA, carryB, err);
-                        fo = q.fo; carryA = q.carryA; carryB = q.carryB; err = q.err;
-                    }
-                    /* park: {p_ref, p_alt} over the row just read, a + b (or the LUT index pair) beside it */
+                    const FragOut fo = score_cfrag_chunk<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, n, m,
+                                                                r, err);
                     double s0 = fo.s;
                     if (ASSOC == SVGT_ASSOC_CLASSIC || (fo.lead > 0 && lane < fo.lead)) s0 = __hiloint2double(fo.ib, fo.ia);
                     ws.spark[g][lane] = s0;
-                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowaddr + (unsigned)g * 528u), "d"(fo.p_ref), "d"(fo.p_alt) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(fo.p_ref) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
                     if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
                 } else {
                     const SplitOut so = score_csplit_chunk<ASSOC>(ws.spf[g], s_pm, lane, n, r);
-                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rowaddr + (unsigned)g * 528u), "d"(so.vseq), "d"(so.vclip) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(so.vseq) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(so.vclip) : "memory");
                     if (so.lead) leads |= (unsigned long long)so.lead << (8 * g);
                 }
             }
@@ -412,8 +383,9 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, 1) svgt_compact_kernel(const S
                 cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
                 const int lead = (int)(leads >> (8 * gb)) & 0xFF;
                 const double *pr = reinterpret_cast<const double *>(&ws.ring[slot][gb][0]);
-                if (!sp) c_replay_frag<ASSOC>(&ws.spark[gb][0], pr, c, cnt, lead, s_pm, acc, pend);
-                else c_replay_split<ASSOC>(pr, c, cnt, lead, acc, pend);
+                if (!sp) c_replay_frag<ASSOC>(c == 0 ? &ws.spark[gb][0] : pr + (c - 1) * 33, &ws.spark[gb][0], c, cnt, lead, s_pm,
+                                              acc, pend);
+                else c_replay_split<ASSOC>(pr + c * 33, cnt, lead, acc, pend);
             }
             leads = 0ull;
             __syncwarp();

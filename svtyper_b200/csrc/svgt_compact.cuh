@@ -13,10 +13,13 @@
  *       (unsigned)(e - w1) < max(len - 2m + 1, 0).  Exact for every int32 input: a wrapped difference is
  *       >= 2^30 while the bound is < 2^14.
  *   contig tests (parsers.py:805,833-834)  are the four class bits of the row.
- * Rows the 16-byte form cannot express directly (gapped reads, spans beyond 14 bits, extra primaries)
- * arrive as EXTRA / MULTI / CONT rows and leave the straight-line chain through one vote, exactly as in
- * the wide-row kernel; there they are decoded into the wide form (decode_wide) and handed to the same
- * resolver / literal-path functions, so those are shared, not duplicated.
+ *   window validity (max(0, pos - m) shortens a window at the contig start: no read can cover it) is a
+ *       per-site mask over the class bits, so such sites take the same chain as every other.
+ * Reads the 16-byte form cannot test on the device (gapped alignments, spans beyond 14 bits) are MULTI rows
+ * whose is_ref_seq outcome the packer evaluated (one bit in the length field); extra primaries of a fragment
+ * are CONT rows.  Both leave the straight-line chain through one vote; p_concordant ties and libraries
+ * outside the integer rewrite are decoded into the wide form (decode_wide) for the literal fp64 row
+ * (slow_row), which is shared with the wide-row kernels.
  */
 #pragma once
 #include "svgt_lean.cuh"
@@ -27,7 +30,7 @@ namespace {
 enum : unsigned {
     CS_SAME = 1u << 5,
     CLS_A_ON_A = 1u << 28, CLS_A_ON_B = 1u << 29, CLS_B_ON_A = 1u << 30, CLS_B_ON_B = 1u << 31,
-    CF_PAIRED = 1u << 25, CF_REV_A = 1u << 26, CF_REV_B = 1u << 27, CF_CONT = 1u << 28, CF_EXTRA = 1u << 29,
+    CF_PAIRED = 1u << 25, CF_REV_A = 1u << 26, CF_REV_B = 1u << 27, CF_CONT = 1u << 28,
     CF_MULTI_A = 1u << 30, CF_MULTI_B = 1u << 31,
     CSP_SOFT = 1u << 16, CSP_FIRST = 1u << 17, CSP_WIDE = 1u << 18, CSP_XEND = 1u << 19
 };
@@ -35,36 +38,30 @@ constexpr int kLenBits = 14;
 constexpr unsigned kLenMask = (1u << kLenBits) - 1u;
 constexpr unsigned kLibMaskC = 0x1FFu;
 
-/* fast-site constants, three warp-uniform LDS.128 */
+/* per-site constants, warp-uniform LDS.128s (two for the one-contig chain, four for the general one) */
 struct CSiteF {
     int wA0, wA1, wB0, wB1;
-    int pat, del, fast, m21;     /* pat: (w3 & 0x2E000000) of an alt-orientation pair; m21 = 2 * min_aligned - 1;
-                                    fast: 0 generic scorer, 1 one contig & not INV, 2 general chain */
+    int pat, del, fast, m21;     /* pat: (w3 & 0x0E000000) of an alt-orientation pair; m21 = 2 * min_aligned - 1;
+                                    fast: 1 one contig, not INV, both is_ref_seq windows valid; 2 general chain */
     int sgnA, sgnB, inv, same;
+    unsigned mAA, mAB, mBA, mBB; /* class bit a read must carry to cover window A / B (0: the window is invalid) */
 };
 
-/* the wide form of a compact fragment row, with invented contig ids (0 = contig A, tB = contig B) */
+/* the wide form of a compact fragment row for the literal path (slow_row): invented contig ids
+ * (0 = contig A, tB = contig B); MULTI rows keep a zero-length interval, their hit is not slow_row's business */
 __device__ __forceinline__ void decode_wide(const int4 r, const int tB, int4 &lo, int4 &hi)
 {
     const unsigned w2 = (unsigned)r.z, w3 = (unsigned)r.w;
     const int tidA = (w2 & CLS_A_ON_A) ? 0 : ((w2 & CLS_A_ON_B) ? tB : -3);
     const int tidB = (w2 & CLS_B_ON_A) ? 0 : ((w2 & CLS_B_ON_B) ? tB : -3);
-    int fl = ((w3 & CF_REV_A) ? F_REV_A : 0) | ((w3 & CF_REV_B) ? F_REV_B : 0) | ((w3 & CF_PAIRED) ? F_PAIRED : 0) |
-             ((w3 & CF_CONT) ? F_CONT : 0);
+    const int lenA = (w3 & CF_MULTI_A) ? 0 : (int)(w2 & kLenMask);
+    const int lenB = (w3 & CF_MULTI_B) ? 0 : (int)((w2 >> kLenBits) & kLenMask);
+    const bool hasB = (w3 & CF_PAIRED) || (w2 & (CLS_B_ON_A | CLS_B_ON_B));
+    lo = make_int4(r.x, r.x + lenA, r.y - lenB, r.y);
+    hi.x = tidA; hi.y = tidB;
     hi.z = (int)((w3 & 0xFFFFu) | (((w3 >> 16) & kLibMaskC) << 16));
-    if (w3 & CF_EXTRA) {
-        fl = F_EXTRA | (fl & F_CONT);
-        if (w3 & CF_MULTI_B) { lo = make_int4(0, 0, r.x, r.y); hi.x = 0; hi.y = tidB; fl |= F_HAS_B; }
-        else { lo = make_int4(r.x, r.y, 0, 0); hi.x = tidA; hi.y = 0; fl |= F_HAS_A; }
-        hi.z &= ~0xFFFF;
-    } else {
-        const int lenA = (int)(w2 & kLenMask), lenB = (int)((w2 >> kLenBits) & kLenMask);
-        const bool hasB = (w3 & CF_PAIRED) || (w2 & (CLS_B_ON_A | CLS_B_ON_B));
-        lo = make_int4(r.x, r.x + lenA, r.y - lenB, r.y);
-        hi.x = tidA; hi.y = tidB;
-        fl |= F_HAS_A | (hasB ? F_HAS_B : 0) | ((w3 & CF_MULTI_A) ? F_MULTI_A : 0) | ((w3 & CF_MULTI_B) ? F_MULTI_B : 0);
-    }
-    hi.w = fl;
+    hi.w = F_HAS_A | (hasB ? F_HAS_B : 0) | ((w3 & CF_REV_A) ? F_REV_A : 0) | ((w3 & CF_REV_B) ? F_REV_B : 0) |
+           ((w3 & CF_PAIRED) ? F_PAIRED : 0) | ((w3 & CF_CONT) ? F_CONT : 0);
 }
 
 /*
@@ -110,7 +107,7 @@ __device__ __forceinline__ void crow_fast(const int4 r, const int4 f0, const int
         "mov.b64 %1, {zr, t};\n\t"
         /* paired-end straddles */
         "and.pred pe0, eA, eB;\n\t"
-        "and.b32 t, %8, 0x2E000000;\n\t"
+        "and.b32 t, %8, 0x0E000000;\n\t"
         "setp.eq.and.s32 pa, t, %13, pe0;\n\t"
         "setp.eq.and.s32 pr0, t, 0x0A000000, pe0;\n\t"
         "sub.s32 d, %5, %16;\n\t"
@@ -168,14 +165,16 @@ __device__ __forceinline__ void crow_fast(const int4 r, const int4 f0, const int
 }
 
 /*
- * The same row for a site whose breakends lie on two contigs and / or an inversion (fast_row_gen()):
- *   %24 sgnA  %25 sgnB  %26 inv
+ * The same row for any other site -- breakends on two contigs, an inversion (the reciprocal orientation also
+ * straddles, singlesample.py:296-303), or a breakend whose is_ref_seq window is cut off by the contig start:
+ *   %24 sgnA  %25 sgnB  %26 inv    %27..%30 class masks of (read A, window A), (A, B), (read B, window A), (B, B)
  */
-__device__ __forceinline__ void crow_gen(const int4 r, const int4 f0, const int4 f1, const int4 f2, const uint4 w0,
-                                         const uint4 w1, double &hA, double &hB, double &wref, double &walt, int &tie)
+__device__ __forceinline__ void crow_gen(const int4 r, const int4 f0, const int4 f1, const int4 f2, const uint4 f3,
+                                         const uint4 w0, const uint4 w1, double &hA, double &hB, double &wref,
+                                         double &walt, int &tie)
 {
     asm("{\n\t"
-        ".reg .pred eaa, eab, eba, ebb, p, q, hA, hB, pe0, pa, prc, pr0, ra, rb, pc, pt, pdel, pinv, both, any, x1, ron, aon, ptrap;\n\t"
+        ".reg .pred eaa, eab, eba, ebb, haa, hab, hba, hbb, p, q, hA, hB, pe0, pa, prc, pr0, ra, rb, pc, pt, pdel, pinv, both, any, x1, ron, aon, ptrap;\n\t"
         ".reg .b32 t, u, d, x, o, k2, len, hb, i1, i2, a1, a2, h1, h2, l19, zr, lmA, lmB;\n\t"
         "mov.b32 zr, 0;\n\t"
         "and.b32 t, %7, 0x3FFF;\n\t"
@@ -192,16 +191,24 @@ __device__ __forceinline__ void crow_gen(const int4 r, const int4 f0, const int4
         "setp.ne.s32 eba, t, 0;\n\t"
         "and.b32 t, %7, 0x80000000;\n\t"
         "setp.ne.s32 ebb, t, 0;\n\t"
-        /* is_ref_seq: on contig A against window A, on contig B against window B */
+        /* is_ref_seq: on contig A against window A, on contig B against window B (valid windows only) */
+        "and.b32 t, %7, %27;\n\t"
+        "setp.ne.s32 haa, t, 0;\n\t"
+        "and.b32 t, %7, %28;\n\t"
+        "setp.ne.s32 hab, t, 0;\n\t"
+        "and.b32 t, %7, %29;\n\t"
+        "setp.ne.s32 hba, t, 0;\n\t"
+        "and.b32 t, %7, %30;\n\t"
+        "setp.ne.s32 hbb, t, 0;\n\t"
         "sub.s32 u, %9, %5;\n\t"
-        "setp.lt.and.u32 p, u, lmA, eaa;\n\t"
+        "setp.lt.and.u32 p, u, lmA, haa;\n\t"
         "sub.s32 u, %11, %5;\n\t"
-        "setp.lt.and.u32 q, u, lmA, eab;\n\t"
+        "setp.lt.and.u32 q, u, lmA, hab;\n\t"
         "or.pred hA, p, q;\n\t"
         "sub.s32 u, %6, %10;\n\t"
-        "setp.lt.and.u32 p, u, lmB, eba;\n\t"
+        "setp.lt.and.u32 p, u, lmB, hba;\n\t"
         "sub.s32 u, %6, %12;\n\t"
-        "setp.lt.and.u32 q, u, lmB, ebb;\n\t"
+        "setp.lt.and.u32 q, u, lmB, hbb;\n\t"
         "or.pred hB, p, q;\n\t"
         "selp.b32 t, 0x3FF00000, 0, hA;\n\t"
         "mov.b64 %0, {zr, t};\n\t"
@@ -209,7 +216,7 @@ __device__ __forceinline__ void crow_gen(const int4 r, const int4 f0, const int4
         "mov.b64 %1, {zr, t};\n\t"
         /* alt straddle: read A on contig A, read B on contig B, alt orientation; INV also the reciprocal one */
         "and.pred pe0, eaa, ebb;\n\t"
-        "and.b32 t, %8, 0x2E000000;\n\t"
+        "and.b32 t, %8, 0x0E000000;\n\t"
         "setp.eq.and.s32 pa, t, %13, pe0;\n\t"
         "sub.s32 d, %5, %16;\n\t"
         "setp.lt.and.u32 pa, d, %17, pa;\n\t"
@@ -280,26 +287,14 @@ __device__ __forceinline__ void crow_gen(const int4 r, const int4 f0, const int4
         : "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w),                                                 /* %5..%8   */
           "r"(f0.x), "r"(f0.y), "r"(f0.z), "r"(f0.w), "r"(f1.x), "r"(f1.y), "r"(f1.w),            /* %9..%15  */
           "r"(w0.x), "r"(w0.y), "r"(w0.z), "r"(w0.w), "r"(w1.x), "r"(w1.y), "r"(w1.z), "r"(w1.w), /* %16..%23 */
-          "r"(f2.x), "r"(f2.y), "r"(f2.z)                                                         /* %24..%26 */);
+          "r"(f2.x), "r"(f2.y), "r"(f2.z), "r"(f3.x), "r"(f3.y), "r"(f3.z), "r"(f3.w)             /* %24..%30 */);
 }
 
-/* is_ref_seq of an EXTRA row's one interval [r.x, r.y) for the slot it names (rare path only) */
-__device__ __forceinline__ void extra_hits(const int4 r, const CSiteF &F, bool &hitA, bool &hitB)
-{
-    const unsigned w2 = (unsigned)r.z, w3 = (unsigned)r.w;
-    const bool slotB = (w3 & CF_MULTI_B) != 0;
-    const bool onA = slotB ? (w2 & CLS_B_ON_A) != 0 : (w2 & CLS_A_ON_A) != 0;
-    const bool onB = slotB ? (w2 & CLS_B_ON_B) != 0 : (w2 & CLS_A_ON_B) != 0;
-    const bool h = (onA && r.x <= F.wA0 && r.y >= F.wA1) || (onB && r.x <= F.wB0 && r.y >= F.wB1);
-    hitA = h && !slotB; hitB = h && slotB;
-}
-
-/* one 32-row fragment chunk of a FAST site (phase A); rows beyond the site's last one are zero */
+/* one 32-row fragment chunk (phase A); rows beyond the site's last one are zero */
 template <int ASSOC>
 __device__ __forceinline__ FragOut score_cfrag_chunk(const SvgtParams &p, const Tables &t, const SiteS &S, const CSiteF &F,
                                                      const WinF *wf, const double *s_pm, const LibK *s_lib, const int lane,
-                                                     const int n, const int g, const int m, const int4 r,
-                                                     unsigned &carryA, unsigned &carryB, int &err)
+                                                     const int n, const int m, const int4 r, int &err)
 {
     const unsigned full = 0xffffffffu;
     const int4 f0 = *reinterpret_cast<const int4 *>(&F.wA0);
@@ -315,34 +310,23 @@ __device__ __forceinline__ FragOut score_cfrag_chunk(const SvgtParams &p, const 
     double hA, hB, wref, walt;                      /* {0,1}, {0,1}, {0,.5,1}, {0,1} */
     int tie;
     if (f1.z == 1) crow_fast(r, f0, f1, w0, w1, hA, hB, wref, walt, tie);
-    else crow_gen(r, f0, f1, *reinterpret_cast<const int4 *>(&F.sgnA), w0, w1, hA, hB, wref, walt, tie);
+    else crow_gen(r, f0, f1, *reinterpret_cast<const int4 *>(&F.sgnA), *reinterpret_cast<const uint4 *>(&F.mAA), w0, w1, hA, hB,
+                  wref, walt, tie);
 
-    /* one vote for everything rare: EXTRA / MULTI / CONT rows, a p_concordant tie or a library the integer
-     * rewrites do not cover; carried EXTRA hits re-enter through the carry bits */
+    /* one vote for everything rare: MULTI rows (the packer's is_ref_seq verdict), CONT rows (extra primaries),
+     * a p_concordant tie or a library the integer rewrites do not cover */
     unsigned vm = 0u, nm = 0u;
     bool special = false;
-    const bool xrow = (z & (CF_EXTRA | CF_MULTI_A | CF_MULTI_B | CF_CONT)) != 0u;
-    if (__any_sync(full, xrow || tie != 0) || (carryA | carryB) != 0u) {
-        if (__any_sync(full, (z & (CF_EXTRA | CF_MULTI_A | CF_MULTI_B)) != 0u) || (((carryA | carryB) >> g) & 1u)) {
-            int fl = ((z & CF_CONT) ? F_CONT : 0) | ((z & CF_EXTRA) ? F_EXTRA : 0);
-            if (z & CF_EXTRA) {
-                bool xa, xb;
-                extra_hits(r, F, xa, xb);
-                hA = xa ? 1.0 : 0.0; hB = xb ? 1.0 : 0.0;
-            } else {
-                fl |= ((z & CF_MULTI_A) ? F_MULTI_A : 0) | ((z & CF_MULTI_B) ? F_MULTI_B : 0);
-            }
-            const MultiOut q = resolve_multi(fl, lane, n, g, (unsigned)__double2hiint(hA), (unsigned)__double2hiint(hB),
-                                             carryA, carryB);
-            hA = __hiloint2double((int)q.hAhi, 0); hB = __hiloint2double((int)q.hBhi, 0);
-            carryA = q.carryA; carryB = q.carryB; nm = q.nm; vm = q.vm;
-            special = nm != vm;
-        } else if (__any_sync(full, xrow)) {            /* CONT rows only */
+    const bool xrow = (z & (CF_MULTI_A | CF_MULTI_B | CF_CONT)) != 0u;
+    if (__any_sync(full, xrow || tie != 0)) {
+        if (z & CF_MULTI_A) hA = ((unsigned)r.z & 1u) ? 1.0 : 0.0;
+        if (z & CF_MULTI_B) hB = (((unsigned)r.z >> kLenBits) & 1u) ? 1.0 : 0.0;
+        if (__any_sync(full, (z & CF_CONT) != 0u)) {    /* who starts a fragment */
             vm = n >= 32 ? full : ((1u << n) - 1u);
             nm = __ballot_sync(full, lane < n && !(z & CF_CONT));
             special = nm != vm;
         }
-        if (tie != 0 && (z & (CF_PAIRED | CF_EXTRA)) == CF_PAIRED) {       /* the literal row */
+        if (tie != 0 && (z & CF_PAIRED)) {              /* the literal row */
             int4 lo, hi;
             decode_wide(r, S.tB, lo, hi);
             bool alt, refA, refB, pc;
@@ -365,6 +349,8 @@ __device__ __forceinline__ FragOut score_cfrag_chunk(const SvgtParams &p, const 
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
         o.ia = hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0;
     } else if (special && ((vm & ~nm) & ~(nm << 1)) == 0u) {
+        /* every continuation row sits right below the row that starts its fragment (and none leads the chunk):
+         * one fold step -- the lower row takes (s_up + a) + b and the weights, the upper row parks zeros */
         const unsigned NN = vm & ~nm;
         const bool cont = (NN >> lane) & 1u, has_next = (NN >> 1 >> lane) & 1u;
         const double us = __shfl_up_sync(full, o.s, 1), ur = __shfl_up_sync(full, o.p_ref, 1);

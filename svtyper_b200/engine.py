@@ -80,6 +80,7 @@ def _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_
     d.unit_mode = int(unit_mode)
     d.split_weight, d.disc_weight = float(split_weight), float(disc_weight)
     d.flags = int(flags)
+    d.rows_min_aligned = int(batch.min_aligned)
     return d
 
 

@@ -64,6 +64,7 @@ class SvgtCBatch(ctypes.Structure):
         ("split_weight", ctypes.c_double), ("disc_weight", ctypes.c_double),
         ("out_final", ctypes.c_void_p), ("done_flag", ctypes.c_void_p),
         ("done_value", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("rows_min_aligned", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 

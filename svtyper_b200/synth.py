@@ -365,10 +365,13 @@ def _gen_chunk(args):
 
 
 def generate_parallel(config="del1m4lib", n_sites=None, rank=0, chunk=25_000, procs=None, alloc=None,
-                      bucket=True) -> ev.EvidenceBatch:
+                      bucket=True, site_range=None) -> ev.EvidenceBatch:
     """`generate()` over independent Philox streams (one per chunk), fanned out over a
     process pool; chunks travel through /dev/shm files, not pickles.  Stream ids are
-    `rank * 65536 + chunk_index`, so every rank of a multi-GPU job draws a distinct shard."""
+    `rank * 65536 + chunk_index`, so every rank of a multi-GPU job draws a distinct shard.
+    `site_range=(lo, hi)` returns only sites [lo, hi) of that batch (same bytes as slicing the
+    whole thing), generating just the chunks that cover them: how the ranks of a site-sharded
+    job each build their shard of ONE global batch without moving it."""
     import multiprocessing as mp
     import tempfile
     cfg = CONFIGS[config]
@@ -376,6 +379,33 @@ def generate_parallel(config="del1m4lib", n_sites=None, rank=0, chunk=25_000, pr
     sizes = [min(chunk, n - i) for i in range(0, n, chunk)] or [0]
     seed = BASE_SEED + cfg["seed_off"]
     libs = make_libraries(cfg["n_lib"])
+    if site_range is not None:
+        lo, hi = int(site_range[0]), int(site_range[1])
+        c0, c1 = lo // chunk, max(lo // chunk, (hi - 1) // chunk) if hi > lo else lo // chunk
+        parts = []
+        sel = [(i, sizes[i]) for i in range(c0, min(c1, len(sizes) - 1) + 1)] if hi > lo else []
+        if sel:
+            pr = procs or min(len(sel), max(1, (os.cpu_count() or 2) - 1), 32)
+            tmp = tempfile.mkdtemp(prefix="svgt_synth_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            jobs = [(config, sz, seed, rank * 65536 + i, os.path.join(tmp, "c%05d" % i)) for i, sz in sel]
+            try:
+                if len(jobs) > 1 and pr > 1:
+                    with mp.get_context("forkserver").Pool(pr) as pool:
+                        pool.map(_gen_chunk, jobs, chunksize=1)
+                else:
+                    for j in jobs:
+                        _gen_chunk(j)
+                for j in jobs:
+                    parts.append(ev.EvidenceBatch(np.load(j[4] + ".sites.npy"), np.load(j[4] + ".frags.npy"),
+                                                  np.load(j[4] + ".splits.npy"), libs))
+            finally:
+                import shutil
+                shutil.rmtree(tmp, ignore_errors=True)
+        if not parts:
+            return generate(config, n_sites=0, seed=seed, rank=rank * 65536, bucket=bucket, libs=libs)
+        whole = concat_batches(parts, None, False)
+        part = whole.slice_sites(lo - c0 * chunk, hi - c0 * chunk)
+        return concat_batches([part], alloc, bucket)
     if len(sizes) == 1:
         return concat_batches([generate(config, n_sites=sizes[0], seed=seed, rank=rank * 65536, bucket=False)],
                               alloc, bucket)

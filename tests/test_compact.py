@@ -26,10 +26,10 @@ def test_roundtrip_scores_identically(oracle, config, n):
         exp = oracle.score(b, assoc_mode=assoc)
         got = oracle.score(w, assoc_mode=assoc)
         assert got.tobytes() == exp.tobytes(), config
-    # rows: every wide row is one compact row, except EXTRA rows (one per slot they hold)
+    # rows: every wide row is one compact row, except EXTRA rows (their verdict rides on the MULTI row)
     skip = (b.sites[:, 9] & ev.SITE_SKIP) != 0
     assert cb.n_split == int(b.sites[~skip, 15].sum())
-    assert cb.n_frag >= int(b.sites[~skip, 12].sum()) - int(((b.frags[:, 7] & ev.F_EXTRA) != 0).sum())
+    assert cb.n_frag == int(b.sites[~skip, 12].sum()) - int(((b.frags[:, 7] & ev.F_EXTRA) != 0).sum())
     assert cb.algorithmic_bytes() == cb.n_sites * 128 + 16 * cb.n_rows
     # second conversion of the decoded batch reproduces the compact rows bit for bit
     cb2 = cp.compact_from_wide(w)
@@ -82,7 +82,9 @@ def test_escapes_long_reads_and_two_slot_extra(oracle):
     ]
     b = _one_site(frags, [])
     cb, w = roundtrip(b)
-    assert cb.n_frag == 6 + 1 + 2      # one more row for the two-slot EXTRA, two escapes
+    assert cb.n_frag == 5              # the EXTRA row and the over-long spans travel as hit bits
+    w3 = cb.rows[:, 3].astype(np.int64) & 0xFFFFFFFF
+    assert int(((w3 & cp.CF_MULTI_A) != 0).sum()) == 2 and int(((w3 & cp.CF_MULTI_B) != 0).sum()) == 2
     exp = oracle.score(b)
     assert exp["RS"][0] >= 4
     assert oracle.score(w).tobytes() == exp.tobytes()
@@ -98,12 +100,21 @@ def test_wide_split_pieces(oracle, n_before):
     b = _one_site([], splits)
     cb, w = roundtrip(b)
     sp = cb.rows[int(cb.sites[0, 10]):]
-    pos = np.nonzero(sp[:, 3] & cp.CSP_WIDE)[0]
+    pos = np.nonzero(sp[:, 3].astype(np.int64) & cp.CSP_WIDE)[0]
     assert pos.size == 2 and not (pos % 32 == 31).any()
     assert ((sp[pos + 1, 3] & cp.CSP_XEND) != 0).all()
     exp = oracle.score(b)
     assert exp["AS"][0] == n_before + 2     # (n + 3) * (1 - 1e-6), truncated
     assert oracle.score(w).tobytes() == exp.tobytes()
+
+
+def test_min_aligned_is_part_of_the_encoding(oracle):
+    b = synth.generate("mixed100k", n_sites=1500, seed=12)
+    for m in (5, 20, 35):
+        cb = cp.compact_from_wide(b, min_aligned=m)
+        assert cb.min_aligned == m
+        got = oracle.score(cp.wide_from_compact(cb), min_aligned=m)
+        assert got.tobytes() == oracle.score(b, min_aligned=m).tobytes(), m
 
 
 def test_library_index_limit():
