@@ -1,18 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- SV breakpoints genotyped / second on N B200s (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is one pass of the scoring path over one resident batch of synthetic evidence:
-config "del1m4lib" (BASELINE.json configs[3]: 1M DEL breakpoints, 4 read-group libraries with
-distinct insert-size histograms, the config the 1->8 GPU site-shard metric is quoted on; it fits
-one GPU).  Each rank holds its own `--sites` breakpoints (weak scaling); with N > 1 every step
-ends with one NCCL gather of the 80-byte output rows to rank 0.  One JSON line on rank 0.
+A step is one pass of the scoring path (svgt_compact_kernel + svgt_call_compact_kernel through the C ABI) over
+one resident batch of synthetic evidence in the compact 16-byte-row schema: config "del1m4lib"
+(BASELINE.json configs[3]: 1M DEL breakpoints, 4 read-group libraries with distinct insert-size histograms;
+it fits one GPU).  With N > 1 the run measures BOTH readings of "1 -> 8 B200 site shard":
+
+  weak    every rank holds its own `--sites` breakpoints (per-GPU work fixed);
+  strong  ONE global batch of `--sites` breakpoints, cut into contiguous site ranges balanced by evidence
+          rows (svtyper_b200/shard.py), rank r scoring range r.
+
+In both, the 80-byte output rows of every rank land in rank 0's buffer: each rank's call kernel stores its rows
+straight into that buffer over NVLink (CUDA IPC peer mapping, one flag per rank; no collective inside the
+step), or -- if peer mapping is unavailable -- through one NCCL gather per step.  `--scaling` picks which of
+the two is the line's `value` (default weak); the other is reported under its own key.  One JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -26,6 +35,7 @@ if REPO not in sys.path:
 
 METRIC = "sv_breakpoints_genotyped_per_sec"
 UNIT = "breakpoints/s"
+INT_FIELDS = ("GT", "GQ", "DP", "RO", "AO", "QR", "QA", "RS", "AS", "ASC", "RP", "AP")
 
 
 def parse_args():
@@ -35,17 +45,22 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="del1m4lib")
-    ap.add_argument("--sites", type=int, default=1_000_000, help="breakpoints per GPU")
+    ap.add_argument("--sites", type=int, default=1_000_000, help="breakpoints per GPU (weak) / in the global batch (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=0, help="sites in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the site-sharded (strong) measurement")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     return ap.parse_args()
 
 
 def workload_name(args):
-    return "%s: %d DEL breakpoints/GPU, 4 libraries, <=1000 reads/site (BASELINE.json configs[3])" % (
-        args.config, args.sites) if args.config == "del1m4lib" else "%s: %d breakpoints/GPU" % (args.config, args.sites)
+    if args.config == "del1m4lib":
+        return "del1m4lib: %d DEL breakpoints, 4 libraries, <=1000 reads/site (BASELINE.json configs[3])" % args.sites
+    if args.config == "stress1m":
+        return "stress1m: %d sites, max_reads=10000 ragged evidence incl. empty and skipped sites (BASELINE.json configs[4])" % args.sites
+    return "%s: %d breakpoints" % (args.config, args.sites)
 
 
 class ClockSampler(threading.Thread):
@@ -111,19 +126,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(sites):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/traffic.json), valid only for the workload size it was captured at."""
+def ncu_traffic(config, sites):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json);
+    only valid for the workload it was captured on, and only reported together with the capture's git hash."""
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
             tr = json.load(f)
-        return tr if int(tr.get("workload_sites", -1)) == int(sites) else None
+        if int(tr.get("workload_sites", -1)) == int(sites) and tr.get("config") == config and tr.get("git"):
+            return tr
     except Exception:
-        return None
-
-
-def cpu_sample_of(batch, n):
-    return batch.slice_sites(0, min(n, batch.n_sites))
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -149,7 +162,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample_sites_per_step": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": pool.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -159,9 +172,176 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+class RowGather(object):
+    """Where every rank's output rows end up: rank 0's buffer.
+
+    peer: rank 0 owns a CUDA-IPC-exported buffer (two halves, alternating by step) plus one flag word per rank;
+          every rank maps both and hands its call kernel `out_final` / `done_flag` pointers into them, so the rows
+          cross NVLink as plain stores and the step needs no collective -- rank 0 just waits for the flags.
+    nccl: one dist.gather of the padded shards per step (the fallback, and the checked alternative).
+    """
+
+    def __init__(self, mode, rank, world, counts, device):
+        import torch
+        import torch.distributed as dist
+        from svtyper_b200 import native
+        self.rank, self.world, self.counts = rank, world, list(counts)
+        self.offsets = [sum(self.counts[:r]) for r in range(world)]
+        self.total = sum(self.counts)
+        self.mode = mode if world > 1 else "none"
+        self.lib = native.lib()
+        self.buf = self.flags = None
+        self._owned = []
+        if self.mode == "peer":
+            ok = 1
+            handles = [None, None]
+            try:
+                if rank == 0:
+                    b, f = ctypes.c_void_p(), ctypes.c_void_p()
+                    hb, hf = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+                    native.check(self.lib.svgt_shared_alloc(2 * max(self.total, 1) * 80, ctypes.byref(b), hb))
+                    native.check(self.lib.svgt_shared_alloc(4096, ctypes.byref(f), hf))
+                    self.buf, self.flags = b.value, f.value
+                    self._owned = [b.value, f.value]
+                    handles = [hb.raw, hf.raw]
+            except Exception as e:      # noqa: BLE001
+                ok = 0
+                self.err = str(e)
+            dist.broadcast_object_list(handles, src=0)
+            if rank != 0 and handles[0] is not None:
+                try:
+                    b, f = ctypes.c_void_p(), ctypes.c_void_p()
+                    native.check(self.lib.svgt_shared_open(handles[0], ctypes.byref(b)))
+                    native.check(self.lib.svgt_shared_open(handles[1], ctypes.byref(f)))
+                    self.buf, self.flags = b.value, f.value
+                except Exception as e:  # noqa: BLE001
+                    ok = 0
+                    self.err = str(e)
+            if handles[0] is None:
+                ok = 0
+            t = torch.tensor([ok], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                self.mode = "nccl"
+        if self.mode == "nccl":
+            pad = max(self.counts)
+            self.pad = pad
+            self.send = [torch.zeros((max(pad, 1), 80), dtype=torch.uint8, device=device) for _ in range(2)]
+            self.recv = [[torch.empty_like(self.send[0]) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
+            self.pending = [None, None]
+        self.step_no = 0
+
+    def arm(self, desc, half):
+        """Point this rank's launch descriptor at its slice of rank 0's buffer for the coming step."""
+        self.step_no += 1
+        if self.mode == "peer":
+            desc.out_final = self.buf + (half * self.total + self.offsets[self.rank]) * 80
+            desc.done_flag = self.flags + 4 * self.rank
+            desc.done_value = self.step_no
+
+    def out_tensor(self, dev_out, half):
+        return self.send[half] if self.mode == "nccl" else dev_out
+
+    def after_score(self, stream, half):
+        import torch.distributed as dist
+        if self.mode == "peer" and self.rank == 0:
+            from svtyper_b200 import native
+            native.check(self.lib.svgt_wait_flags(ctypes.c_void_p(self.flags), self.world, self.step_no,
+                                                  ctypes.c_void_p(stream.cuda_stream)))
+        elif self.mode == "nccl":
+            self.pending[half] = dist.gather(self.send[half], self.recv[half], dst=0, async_op=True)
+
+    def before_score(self, half):
+        if self.mode == "nccl" and self.pending[half] is not None:
+            self.pending[half].wait()
+            self.pending[half] = None
+
+    def drain(self):
+        if self.mode == "nccl":
+            for h in (0, 1):
+                self.before_score(h)
+
+    def gathered_rows(self, half):
+        """rank 0: all ranks' rows of the last step written into `half`, as OUT_DTYPE numpy rows."""
+        import numpy as np
+        import torch
+        from svtyper_b200 import evidence as ev
+        if self.rank != 0:
+            return None
+        if self.mode == "peer":
+            from svtyper_b200 import native
+            host = np.empty(self.total * 80, dtype=np.uint8)
+            torch.cuda.synchronize()
+            native.check(self.lib.svgt_memcpy_d2h(ctypes.c_void_p(host.ctypes.data),
+                                                  ctypes.c_void_p(self.buf + half * self.total * 80), self.total * 80))
+            return host.view(ev.OUT_DTYPE).copy()
+        parts = [self.recv[half][r][:self.counts[r]].cpu().numpy() for r in range(self.world)]
+        return np.concatenate(parts, axis=0).reshape(-1).view(ev.OUT_DTYPE).copy()
+
+    def close(self):
+        if self.mode == "peer":
+            if self.rank == 0:
+                for p in self._owned:
+                    self.lib.svgt_shared_free(ctypes.c_void_p(p))
+            else:
+                self.lib.svgt_shared_close(ctypes.c_void_p(self.buf))
+                self.lib.svgt_shared_close(ctypes.c_void_p(self.flags))
+
+
+def timed_steps(eng, dev, gather, steps, warmup, world, local_rank, stream):
+    """W warm-up + K timed steps of one resident batch; returns (ms_total max over ranks, per-step kernel ms,
+    clocks, launches).  Every step ends with this rank's rows in rank 0's buffer."""
+    import torch
+    import torch.distributed as dist
+
+    def step(i):
+        half = i & 1
+        gather.before_score(half)
+        gather.arm(dev.desc, half)
+        eng.score(dev, stream, out=gather.out_tensor(dev.out, half))
+        gather.after_score(stream, half)
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    gather.drain()
+    torch.cuda.synchronize()
+    eng.check(dev)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record(stream)
+    for i in range(steps):
+        half = i & 1
+        gather.before_score(half)
+        gather.arm(dev.desc, half)
+        k_ev[i][0].record(stream)
+        eng.score(dev, stream, out=gather.out_tensor(dev.out, half))
+        k_ev[i][1].record(stream)
+        gather.after_score(stream, half)
+    gather.drain()
+    ev1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    kern_ms = [a.elapsed_time(b) for a, b in k_ev]
+    if world > 1:
+        tt = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    eng.check(dev)
+    return ms_total, kern_ms, clocks, eng.launches - launches0, (steps - 1) & 1
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
-    from svtyper_b200 import evidence as ev, synth
+    from svtyper_b200 import compact as cp, evidence as ev, shard, synth
 
     # ---- CPU baseline first (before CUDA is initialised in this process); rank 0, N = 1 only
     cpu = None
@@ -193,13 +373,11 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from svtyper_b200 import engine, native
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.variant >= 0:
-        native.set_variant(args.variant)
-    variant = native.set_variant(args.variant if args.variant >= 0 else -1)
+        dist.init_process_group("nccl", device_id=device)
 
-    # ---- synthetic evidence, generated straight into pinned host memory
+    # ---- synthetic evidence, converted to the compact schema straight into pinned host memory
     pinned = {}
 
     def alloc(name, shape, dtype):
@@ -209,88 +387,89 @@ def run_ours(args, rank, world, local_rank):
 
     procs = max(2, min(32, cores // max(world, 1) - 1))
     t_gen = time.time()
-    batch = synth.generate_parallel(args.config, n_sites=args.sites, rank=rank, procs=procs, alloc=alloc)
+    wide = synth.generate_parallel(args.config, n_sites=args.sites, rank=rank, procs=procs)
+    batch = cp.compact_from_wide(wide, alloc=alloc)
+    del wide
     t_gen = time.time() - t_gen
 
     eng = engine.Engine(local_rank)
-    dev = eng.upload(batch)
     stream = torch.cuda.current_stream()
-    # N > 1: the one collective of the path -- a gather of the 80-byte rows to rank 0 -- is
-    # double-buffered, so the gather of step i runs on NCCL's stream under the kernels of step i+1
-    outs = [dev.out, torch.empty_like(dev.out)] if world > 1 else [dev.out]
-    gathered = [[torch.empty_like(dev.out) for _ in range(world)] for _ in outs] if (world > 1 and rank == 0) \
-        else [None for _ in outs]
-    pending = [None for _ in outs]
+    dev = eng.upload(batch)
 
-    def step(i):
-        b = i % len(outs)
-        if pending[b] is not None:
-            pending[b].wait()                 # the stream (not the host) waits for the gather that read outs[b]
-            pending[b] = None
-        eng.score(dev, stream, out=outs[b])
-        if world > 1:
-            pending[b] = dist.gather(outs[b], gathered[b], dst=0, async_op=True)
-
-    def drain():
-        for b in range(len(outs)):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    drain()
-    torch.cuda.synchronize()
-    eng.check(dev)
-
-    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
-    launches0 = eng.launches
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    ev0.record(stream)
-    for i in range(args.steps):
-        b = i % len(outs)
-        if pending[b] is not None:
-            pending[b].wait()
-            pending[b] = None
-        k_ev[i][0].record(stream)
-        eng.score(dev, stream, out=outs[b])
-        k_ev[i][1].record(stream)
-        if world > 1:
-            pending[b] = dist.gather(outs[b], gathered[b], dst=0, async_op=True)
-    drain()
-    ev1.record(stream)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    kern_ms = [a.elapsed_time(b) for a, b in k_ev]
-    launches = eng.launches - launches0
-    if world > 1:
-        tt = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
-    eng.check(dev)
+    # ---- weak: every rank its own batch, all rows to rank 0
+    counts = [batch.n_sites] * world
+    gather = RowGather(args.gather, rank, world, counts, device)
+    ms_total, kern_ms, clocks, launches, last_half = timed_steps(eng, dev, gather, args.steps, args.warmup, world, local_rank,
+                                                                 stream)
+    weak_value = world * batch.n_sites * args.steps / (ms_total * 1e-3)
+    dev.desc.out_final = None                         # one plain pass: this rank's rows in its own buffer
+    dev.desc.done_flag = None
+    eng.score(dev, stream)
+    own_rows = eng.rows(dev)
+    weak_gather_ok = None
+    if world > 1 and rank == 0:
+        g = gather.gathered_rows(last_half)
+        weak_gather_ok = bool(g[:batch.n_sites].tobytes() == own_rows.tobytes() and g.shape[0] == sum(counts))
+    gather_mode = gather.mode
+    gather.close()
 
     # ---- parity on the CPU sample (same sites, scored by the reference above)
     parity = None
     if cpu_rows is not None:
-        got = eng.rows(dev)[:cpu_sample.n_sites]
-        ok = all(np.array_equal(got[k], cpu_rows[k]) for k in
-                 ("GT", "GQ", "DP", "RO", "AO", "QR", "QA", "RS", "AS", "ASC", "RP", "AP"))
+        got = own_rows[:cpu_sample.n_sites]
+        ok = all(np.array_equal(got[k], cpu_rows[k]) for k in INT_FIELDS)
         ok = ok and bool(np.allclose(got["GL"], cpu_rows["GL"], rtol=0, atol=1e-6))
         parity = {"sites": int(cpu_sample.n_sites), "int_fields_bit_exact_and_GL_1e-6": bool(ok)}
 
-    # ---- end to end through the host-buffer C ABI call (pinned host -> H2D -> kernel -> D2H)
+    # ---- strong: rank 0's batch is THE global batch; rank r scores its row-balanced site range of it
+    strong = None
+    if world > 1 and not args.no_strong:
+        bounds = [0] * (world + 1)
+        if rank == 0:
+            bounds = shard.shard_bounds(batch, world)
+        dist.broadcast_object_list(bounds, src=0)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        if rank == 0:
+            my = batch.slice_sites(lo, hi)
+        else:
+            w = synth.generate_parallel(args.config, n_sites=args.sites, rank=0, procs=procs, site_range=(lo, hi), bucket=False)
+            my = cp.compact_from_wide(w)
+            del w
+        my.order = my.length_order()
+        rows_per_rank = [0] * world
+        t_rows = torch.zeros(world, dtype=torch.int64, device=device)
+        t_rows[rank] = my.n_rows
+        dist.all_reduce(t_rows)
+        rows_per_rank = [int(x) for x in t_rows.tolist()]
+        sdev = eng.upload(my)
+        scounts = [bounds[r + 1] - bounds[r] for r in range(world)]
+        sg = RowGather(args.gather, rank, world, scounts, device)
+        s_ms, s_kern, s_clocks, s_launches, s_half = timed_steps(eng, sdev, sg, args.steps, args.warmup, world, local_rank, stream)
+        s_parity = None
+        if rank == 0:
+            g = sg.gathered_rows(s_half)
+            s_parity = {"sites": int(g.shape[0]),
+                        "sharded_rows_byte_identical_to_one_gpu": bool(g.tobytes() == own_rows.tobytes())}
+        mean_rows = sum(rows_per_rank) / float(world)
+        strong = {"value": args.sites * args.steps / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / args.steps,
+                  "sites_total": int(args.sites), "sites_per_rank": scounts, "rows_per_rank": rows_per_rank,
+                  "row_imbalance": (max(rows_per_rank) / mean_rows - 1.0) if mean_rows else 0.0,
+                  "kernel_ms_avg_rank0": sum(s_kern) / len(s_kern), "gather": sg.mode, "parity": s_parity,
+                  "partition": "shard.shard_bounds: contiguous site ranges balanced by evidence rows"}
+        sg.close()
+        del sdev
+
+    # ---- end to end through the host-buffer C ABI call (pinned host -> H2D -> kernels -> D2H)
     arrs = engine.host_arrays(batch)
+    for k in ("sites", "rows"):
+        arrs[k] = pinned[k]
+    for k, a in list(arrs.items()):
+        if k not in ("sites", "rows"):
+            t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory()
+            arrs[k] = t
     out_pinned = torch.empty((batch.n_sites, ev.OUT_BYTES), dtype=torch.uint8, pin_memory=True)
     eng.score_host(batch, arrays=arrs, out=out_pinned)            # warm: allocates the staging buffers
+    l0 = eng.launches
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -298,37 +477,57 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.e2e_steps):
         eng.score_host(batch, arrays=arrs, out=out_pinned)
     t_e2e = time.perf_counter() - t0
+    e2e_launches = eng.launches - l0
     if world > 1:
         tt = torch.tensor([t_e2e], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.item())
+    e2e_same = bool(out_pinned.numpy().reshape(-1).view(ev.OUT_DTYPE).tobytes() == own_rows.tobytes())
     e2e_value = world * batch.n_sites * args.e2e_steps / t_e2e
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(eng.last_h2d),
            "d2h_bytes_per_step": int(eng.last_d2h), "ms_per_step": 1e3 * t_e2e / args.e2e_steps,
-           "kernel_ms_inside": float(eng.last_kernel_ms), "api": "svgt_ctx_score_host (Engine.score_host), pinned host buffers"}
+           "kernel_ms_inside": float(eng.last_kernel_ms), "gpu_launches": e2e_launches,
+           "rows_identical_to_resident_path": e2e_same,
+           "api": "svgt_ctx_score_host_compact (Engine.score_host), pinned host buffers, 8 site slices pipelined over 3 streams"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
         alg = batch.algorithmic_bytes()
+        surv = batch.survey_bytes()
         k_avg = sum(kern_ms) / len(kern_ms)
         achieved = alg / (k_avg * 1e-3) / 1e9
-        tr = ncu_traffic(batch.n_sites)
+        tr = ncu_traffic(args.config, batch.n_sites)
+        primary_strong = args.scaling == "strong" and strong is not None
+        value = strong["value"] if primary_strong else weak_value
+        ms_step = strong["ms_per_step"] if primary_strong else ms_total / args.steps
+        weak = {"value": weak_value, "unit": UNIT, "ms_per_step": ms_total / args.steps, "sites_per_gpu": batch.n_sites,
+                "gather": gather_mode, "gathered_rows_match": weak_gather_ok}
         line = {
-            "metric": METRIC, "value": world * batch.n_sites * args.steps / (ms_total * 1e-3), "unit": UNIT,
+            "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if primary_strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sites_per_gpu": batch.n_sites,
+            "config": {"workload": workload_name(args), "sites_per_gpu": batch.n_sites, "schema": "compact (16 B rows, 48 B site rows)",
                        "fragment_rows_per_gpu": batch.n_frag, "split_rows_per_gpu": batch.n_split,
-                       "algorithmic_bytes_per_gpu": alg, "l2": "inputs (%.2f GB) larger than L2" % (alg / 1e9),
-                       "kernel_variant": variant, "gather": "nccl gather of 80 B rows to rank 0 every step, double-buffered under the next step" if world > 1 else "none",
+                       "algorithmic_bytes_per_gpu": alg, "survey_8d_bytes_per_gpu": surv,
+                       "l2": "inputs (%.2f GB) larger than L2" % (alg / 1e9),
+                       "gather": {"peer": "call kernels store their 80 B rows straight into rank 0's CUDA-IPC-mapped buffer over NVLink, one flag per rank; no collective in the step",
+                                  "nccl": "nccl gather of 80 B rows to rank 0 every step, double-buffered under the next step",
+                                  "none": "none"}[gather_mode],
                        "gen_seconds": round(t_gen, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "kernel_ms_avg": k_avg, "kernel_ms_min": min(kern_ms),
+                         "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": ({"file": "profiles/traffic.json", "git": tr["git"], "capture": tr.get("capture")} if tr else None),
+                         "peak_source": peak_src, "kernel_ms_avg": k_avg, "kernel_ms_min": min(kern_ms),
+                         "algorithmic_bytes": "48 B/site + 16 B/row (fragment and split rows) + 80 B/site out",
+                         "frac_on_survey_8d_bytes": surv / (k_avg * 1e-3) / 1e9 / peak,
+                         "survey_8d_formula": "48 + 16 F + 32 S + 80 bytes per site",
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
+        if world > 1:
+            line["weak"] = weak
+            line["strong"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

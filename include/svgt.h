@@ -179,6 +179,7 @@ int svgt_shared_open(const unsigned char handle[64], void **dev_ptr);
 int svgt_shared_close(void *dev_ptr);
 int svgt_shared_free(void *dev_ptr);
 int svgt_wait_flags(const int32_t *flags, int32_t n, int32_t value, void *stream);
+int svgt_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes);   /* synchronous read-back of such a buffer */
 
 #ifdef __cplusplus
 }

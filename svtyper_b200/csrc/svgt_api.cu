@@ -562,6 +562,14 @@ int svgt_shared_close(void *dev_ptr)
     return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
 }
 
+int svgt_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) return fail(SVGT_ERR_ARG, "bad %s", "svgt_memcpy_d2h arguments");
+    if (bytes == 0) return SVGT_OK;
+    cudaError_t e = cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "cudaMemcpy(D2H)");
+}
+
 int svgt_shared_free(void *dev_ptr)
 {
     if (!dev_ptr) return SVGT_OK;

@@ -349,27 +349,43 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
             const int step = sp ? k - nsf : k;
             const int *cnts = &ws.cnt[sp ? 1 : 0][0];
             const unsigned slotaddr = ring0 + slot * (unsigned)(G * 528);
-#pragma unroll 1
-            for (int g = 0; g < G; ++g) {
-                const int n = cnts[g] - step * 32;
-                if (n <= 0) continue;
-                const unsigned site_addr = slotaddr + (unsigned)g * 528u;
+            auto load_row = [&](const int g, const int n) -> int4 {
                 int4 r;
                 asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                             : "r"(site_addr + (unsigned)lane * 16u));
+                             : "r"(slotaddr + (unsigned)g * 528u + (unsigned)lane * 16u));
                 if (lane >= n) r = make_int4(0, 0, 0, 0);   /* the copy stopped at the site's last row */
-                __syncwarp();                               /* every lane holds its row: the site's bytes are free to park in */
-                const unsigned pk = site_addr + (unsigned)lane * 8u;
-                if (!sp) {
-                    const FragOut fo = score_cfrag_chunk<ASSOC>(p, t, ws.site[g], ws.sf[g], &ws.wf[g][0], s_pm, s_lib, lane, n, m,
-                                                                r, err);
-                    double s0 = fo.s;
-                    if (ASSOC == SVGT_ASSOC_CLASSIC || (fo.lead > 0 && lane < fo.lead)) s0 = __hiloint2double(fo.ib, fo.ia);
-                    ws.spark[g][lane] = s0;
-                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(fo.p_ref) : "memory");
-                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
-                    if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
-                } else {
+                return r;
+            };
+            auto park_frag = [&](const int g, const FragOut &fo) {
+                const unsigned pk = slotaddr + (unsigned)g * 528u + (unsigned)lane * 8u;
+                double s0 = fo.s;
+                if (ASSOC == SVGT_ASSOC_CLASSIC || (fo.lead > 0 && lane < fo.lead)) s0 = __hiloint2double(fo.ib, fo.ia);
+                ws.spark[g][lane] = s0;
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(fo.p_ref) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
+                if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
+            };
+            if (!sp) {
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const int n = cnts[g] - step * 32;
+                    if (n <= 0) continue;
+                    const int4 r = load_row(g, n);
+                    __syncwarp();
+                    const CSiteF &F = ws.sf[g];
+                    CRow a;
+                    crow_stage1(F, &ws.wf[g][0], s_pm, r, F.fast != 1, a);
+                    if (__any_sync(full, crow_is_rare(r, a))) crow_stage2(p, t, ws.site[g], F, s_lib, lane, n, m, r, a, err);
+                    park_frag(g, crow_stage3<ASSOC>(lane, n, r, a));
+                }
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const int n = cnts[g] - step * 32;
+                    if (n <= 0) continue;
+                    const int4 r = load_row(g, n);
+                    __syncwarp();
+                    const unsigned pk = slotaddr + (unsigned)g * 528u + (unsigned)lane * 8u;
                     const SplitOut so = score_csplit_chunk<ASSOC>(ws.spf[g], s_pm, lane, n, r);
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(so.vseq) : "memory");
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(so.vclip) : "memory");

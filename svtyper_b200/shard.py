@@ -17,7 +17,10 @@ def shard_bounds(batch, world):
     n = batch.n_sites
     if n == 0:
         return [0] * (world + 1)
-    work = batch.sites[:, 12].astype(np.int64) + batch.sites[:, 15].astype(np.int64) + 4   # + fixed per-site cost
+    if hasattr(batch, "work"):                        # CompactBatch
+        work = batch.work() + 4
+    else:
+        work = batch.sites[:, 12].astype(np.int64) + batch.sites[:, 15].astype(np.int64) + 4   # + fixed per-site cost
     csum = np.cumsum(work)
     bounds = [0]
     for r in range(1, world):
