@@ -16,7 +16,8 @@
  *
  * Plain C: pointers and sizes only, no torch / C++ types.  All entry points return 0 on
  * success or a negative svgt_err code, never throw, and are re-entrant per stream.
- * Row layouts are documented in svtyper_b200/evidence.py and DESIGN.md.
+ * Row layouts are documented in svtyper_b200/compact.py (the default, compact schema), svtyper_b200/evidence.py
+ * (the wide interchange schema) and DESIGN.md.
  */
 #ifndef SVGT_H
 #define SVGT_H
@@ -140,15 +141,10 @@ int svgt_score_compact(const svgt_cbatch_t *batch, void *out_rows, int32_t *stat
 int svgt_launches_per_batch(const svgt_batch_t *batch);
 
 /*
- * Kernel variant (same results, different mapping / memory path):
- * 0 = thread-per-site, per-lane 128-bit global loads with register prefetch; 1 = thread-per-site,
- * per-lane cp.async.bulk (TMA 1-D) ring in shared memory; 2 / 3 = warp-cooperative (row per lane,
- * ordered sums interleaved over 8 / 4 sites per warp), tally + call kernels; 4 = warp-cooperative with
- * rows through a cp.async.bulk shared-memory ring; 5 = warp-cooperative with the lean row scorer and a
- * cp.async row ring (the default: 8 sites per work unit after a 1-2-4 ramp that spreads the heaviest
- * sites one per warp); 6 / 7 = variant 5 pinned to 8 / 2 sites per unit.  -1 restores the default (or the
- * SVGT_VARIANT environment variable).  Returns the variant now in force.  Variants 0-4 are kept as
- * parity cross-checks.
+ * Variant of the WIDE-row kernel behind svgt_score_batch() (kept as an independent cross-check of the default
+ * compact path; same results): 0 = thread-per-site, per-lane 128-bit global loads with register prefetch;
+ * 1 = thread-per-site, per-lane cp.async.bulk (TMA 1-D) ring in shared memory.  -1 restores the default (0, or
+ * the SVGT_VARIANT environment variable).  Returns the variant now in force.
  */
 int svgt_set_variant(int variant);
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SVGT_PACK_ABI_VERSION 1
+#define SVGT_PACK_ABI_VERSION 2
 
 enum svgt_pack_err {
     SVGT_PACK_OK = 0,
@@ -103,6 +103,34 @@ int svgt_bam_scan_hist(const svgt_bam_t *bam, int32_t lib, const int32_t **keys,
 /* Row buffers of the last svgt_pack_sites(): [n_frag][8] and [n_split][8] int32 words. */
 int svgt_pack_rows(const svgt_bam_t *bam, const int32_t **frags, int64_t *n_frag, const int32_t **splits,
                    int64_t *n_split);
+
+/*
+ * Wide rows (svtyper_b200/evidence.py: what svgt_pack_sites() and the Python gather emit) -> the compact
+ * 16-byte rows libsvgt.so's default kernel streams (svtyper_b200/compact.py is the specification; its numpy
+ * converter is the parity checker).  Two calls, so the caller can allocate the destination (e.g. pinned host
+ * memory) in between: svgt_compact_count() fills counts[n_sites][2] = compact fragment / split rows per site
+ * and row_off[n_sites + 1] = their prefix sum; svgt_compact_fill() writes out_sites[n_sites][12] and
+ * out_rows[row_off[n_sites]][4].  `min_aligned` is the -m the is_ref_seq bits of gapped reads are evaluated
+ * with (reference parsers.py:801-816).  Sites are independent: blocks of them go to `n_threads` threads.
+ */
+int svgt_compact_count(const int32_t *sites, int64_t n_sites, const int32_t *frags, int64_t n_frag, const int32_t *splits,
+                       int64_t n_split, int32_t min_aligned, int32_t n_threads, int64_t *row_off, int32_t *counts);
+int svgt_compact_fill(const int32_t *sites, int64_t n_sites, const int32_t *frags, int64_t n_frag, const int32_t *splits,
+                      int64_t n_split, int32_t min_aligned, int32_t n_threads, const int64_t *row_off, const int32_t *counts,
+                      int32_t *out_sites, int32_t *out_rows);
+
+/*
+ * FORMAT text of `n` scored 80-byte rows (svgt_out_row_t), the vectorised twin of Genotype.set_format +
+ * get_gt_string (reference parsers.py:375-398) for the values bayesian_genotype() produces
+ * (singlesample.py:406-473): `order[n_fields]` lists the fields in header order (0 GT 1 GQ 2 SQ 3 GL 4 DP 5 RO
+ * 6 AO 7 QR 8 QA 9 RS 10 AS 11 ASC 12 RP 13 AP 14 AB); style[i] = 0 every field of a scored row (GT / GQ / SQ
+ * read "./." / "." / "." when the row is not called), 1 the blank row (blank_genotype_result()), 2 "./." and "."
+ * for every other field.  Floats print as %0.2f, GL as %.0f, AB as %.2g of QA / (QR + QA).  Row i's text goes to
+ * out + i * stride (no terminator), its length to lengths[i].  svgt_format_quals() does %0.2f of QUAL values.
+ */
+int svgt_format_calls(const void *rows, int64_t n, const int32_t *order, int32_t n_fields, const uint8_t *style,
+                      int32_t n_threads, char *out, int64_t stride, int32_t *lengths);
+int svgt_format_quals(const double *qual, int64_t n, char *out, int64_t stride, int32_t *lengths);
 
 #ifdef __cplusplus
 }

@@ -7,8 +7,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["svgt_kernels.cu", "svgt_coop.cu", "svgt_ring.cu", "svgt_lean.cu", "svgt_compact.cu", "svgt_api.cu"]
-HEADERS = ["svgt_kernels.cuh", "svgt_device.cuh", "svgt_coop.cuh", "svgt_lean.cuh", "svgt_compact.cuh", os.path.join("..", "..", "include", "svgt.h")]
+SOURCES = ["svgt_kernels.cu", "svgt_compact.cu", "svgt_api.cu"]
+HEADERS = ["svgt_kernels.cuh", "svgt_device.cuh", "svgt_compact.cuh", os.path.join("..", "..", "include", "svgt.h")]
 LIB_PATH = os.path.join(HERE, "libsvgt.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",

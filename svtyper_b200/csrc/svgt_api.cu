@@ -1,9 +1,11 @@
 /*
  * svgt_api.cu -- the C ABI of libsvgt.so (declared in include/svgt.h).
  *
- * svgt_score_batch() replaces, for a whole batch of breakpoints, the per-breakpoint
- * calls tally_variant_read_fragments + bayesian_genotype of the reference
- * (svtyper/singlesample.py:523-536, :486-498; inlined in svtyper/classic.py:286-495).
+ * svgt_score_compact() (the default path: compact 16-byte rows, svgt_compact.cu) and svgt_score_batch()
+ * (wide 32-byte rows, the thread-per-site kernel of svgt_kernels.cu kept as an independent cross-check)
+ * replace, for a whole batch of breakpoints, the per-breakpoint calls tally_variant_read_fragments +
+ * bayesian_genotype of the reference (svtyper/singlesample.py:523-536, :486-498; inlined in
+ * svtyper/classic.py:286-495).
  * There is no CPU fallback: without a CUDA device every compute entry point returns
  * SVGT_ERR_NO_DEVICE.
  */
@@ -39,7 +41,7 @@ int current_variant()
         int v = atoi(env);
         if (v >= 0 && v < SVGT_VAR_COUNT) return v;
     }
-    return SVGT_VAR_LEAN;
+    return SVGT_VAR_DIRECT;
 }
 
 int check_batch(const svgt_batch_t *b)
@@ -104,8 +106,7 @@ int svgt_launches_per_batch(const svgt_batch_t *batch)
 {
     if (!batch) return fail(SVGT_ERR_ARG, "null batch%s", nullptr);
     if (batch->n_sites <= 0) return 0;
-    if (current_variant() >= SVGT_VAR_LEAN) return svgt_lean_launches();
-    return current_variant() >= SVGT_VAR_COOP ? 2 : 1;      /* tally + call kernels, or one fused kernel */
+    return 1;                                               /* the thread-per-site kernel tallies and calls in one launch */
 }
 
 int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, void *stream)
@@ -136,8 +137,7 @@ int svgt_score_batch(const svgt_batch_t *b, void *out_rows, int32_t *status, voi
     p.n_tiles = (int)((b->n_sites + 31) / 32);
     p.hist_in_smem = (b->n_hist <= SVGT_SMEM_HIST_WORDS) ? 1 : 0;
     const int variant = current_variant();
-    e = (cudaError_t)(variant >= SVGT_VAR_LEAN ? svgt_launch_lean(p, variant, st) : variant == SVGT_VAR_RING ? svgt_launch_ring(p, st)
-                      : variant >= SVGT_VAR_COOP ? svgt_launch_coop(p, variant, st) : svgt_launch_score(p, variant, st));
+    e = (cudaError_t)svgt_launch_score(p, variant, st);
     if (e != cudaSuccess) return cuda_fail(e, "svgt_score_kernel launch");
     return SVGT_OK;
 }

@@ -22,9 +22,179 @@
  * (slow_row), which is shared with the wide-row kernels.
  */
 #pragma once
-#include "svgt_lean.cuh"
+#include "svgt_device.cuh"
 
 namespace {
+
+/* ---- pieces shared by the scorers below ---- */
+constexpr int kWLibs = 4;           /* libraries with per-site windows cached in shared memory */
+
+/* per-(warp, g) site scalars, read warp-uniformly.  First 32 bytes are the hot ones. */
+struct SiteS {
+    int tA, tB, wA0, wA1;
+    int wB0, wB1, meta, var_length;
+    int posA, posB, ciA0, ciA1;
+    int ciB0, ciB1, dAB, nf;
+    long long foff, soff;
+    int ns, slot, pad1, pad2;
+};  /* 96 B */
+
+__device__ __forceinline__ void set_win(unsigned &lo_out, unsigned &w1_out, int lo, int hi, bool enable)
+{
+    lo_out = (unsigned)lo;
+    w1_out = (enable && hi >= lo) ? (unsigned)(hi - lo) + 1u : 0u;
+}
+
+
+/* everything the integer fast path does not cover, evaluated the long way for one row:
+ * libraries beyond the window cache or not provably integer-exact, histogram counts >= 2^26,
+ * breakends within min_aligned of the contig start, malformed DEL lengths, p_concordant ties */
+__device__ __noinline__ void slow_row(const SvgtParams &p, const Tables &t, const SiteS &S, const int4 lo,
+                                      const int4 hi, const LibK *s_lib, int m, int &err, bool &alt, bool &refA,
+                                      bool &refB, bool &pc)
+{
+    const int lib = (int)(((unsigned)hi.z) >> 16);
+    if (lib >= p.n_lib) { err = SVGT_ERR_LIB_INDEX; alt = refA = refB = pc = false; return; }
+    LibK Ls;
+    if (lib >= SVGT_SMEM_LIBS) { int e = 0; Ls = derive_lib(p, lib, &e); }
+    const LibK &L = (lib < SVGT_SMEM_LIBS) ? s_lib[lib] : Ls;
+    const int svtype = S.meta & 3;
+    const bool is_del = svtype == SV_DEL;
+    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1;
+    const bool small_del = is_del && ((double)((long long)S.posB - S.posA) < L.two_sd);
+    alt = !small_del && straddle_literal(lo, hi, S.tA, S.posA, S.ciA0, S.ciA1, S.tB, S.posB, S.ciB0, S.ciB1, o1, o2,
+                                         m, L.flank);
+    if (svtype == SV_INV)
+        alt = alt || straddle_literal(lo, hi, S.tA, S.posA, S.ciA0, S.ciA1, S.tB, S.posB, S.ciB0, S.ciB1, !o1, !o2, m,
+                                      L.flank);
+    refA = !small_del && straddle_literal(lo, hi, S.tA, S.posA, 0, 0, S.tA, S.posA, 0, 0, 0, 1, m, L.flank);
+    refB = !small_del && straddle_literal(lo, hi, S.tB, S.posB, 0, 0, S.tB, S.posB, 0, 0, 0, 1, m, L.flank);
+    pc = p_concordant(t, L, lo.x, lo.w, is_del, S.var_length);
+}
+
+/* one 32-row fragment chunk of site S scored by the warp (phase A): what every lane parks for its row */
+struct FragOut {
+    double s, p_ref, p_alt;         /* ref_seq / ref_span / alt_span addends this row parks (see below)     */
+    int ia, ib;                     /* prob_mapq LUT indices of the row's own ref_seq addends a, b (0 = none) */
+    int lead;                       /* warp-uniform: leading rows that continue the previous chunk's fragment */
+    bool need_idx;                  /* warp-uniform: phase B may read ia / ib of this chunk (lean kernel only)  */
+};
+
+/*
+ * Continuation rows are resolved HERE, lane-parallel, so that phase B is one add per row:
+ * in the sso order (singlesample.py:254-259, :367-378) a fragment's reads are summed into a sub-total
+ * first -- sub = ((0 + a1) + b1) + a2 ... over its rows (CONT rows; EXTRA interval rows add nothing) --
+ * and the sub-total is added to the site sum when the next fragment starts.  The running sub-total is
+ * folded forward along each fragment's rows with shuffles, in row order, and parked in the fragment's
+ * LAST row of the chunk; its earlier rows park 0.0 (x + 0.0 is exact), so phase B just does
+ * acc += pend, pend = s for every row and a fragment that continues in the next chunk stays pending.
+ * Only continuation rows at the very start of a chunk (their fragment began in the previous chunk) are
+ * left to phase B: `lead` of them update the carried sub-total first.
+ */
+struct SplitOut { double vseq, vclip; int lead; };
+
+/* sums parked in the site's output row between the two launches */
+struct ParkedSums { double ref_seq, alt_seq, alt_clip, ref_span, alt_span; };
+
+
+constexpr unsigned kOneHi = 0x3FF00000u, kHalfHi = 0x3FE00000u;   /* high words of 1.0 and 0.5 */
+constexpr unsigned kTrapLk = 0x80000000u;
+constexpr int kHistLenBits = 14;                                  /* packed hist length < 16384 */
+
+/* per-(site, library slot); slot kWLibs is the trap entry for library indices beyond the cache */
+struct WinF {
+    unsigned altA_lo, altA_w1, altB_lo, altB_w1;
+    unsigned FL, FL1, Lk, hpk;   /* hpk = shared byte address of the library's counts | len << 18 */
+};
+
+/* per-CTA: where the lean copy of a cached library's histogram lives */
+struct LibF { unsigned addr; int len; int ok; int pad; };
+
+__device__ __forceinline__ WinF make_winf(const SiteS &S, const LibK &L, const LibF &F, int m, unsigned zero_addr)
+{
+    WinF w;
+    const int svtype = S.meta & 3;
+    const bool is_del = svtype == SV_DEL;
+    const int Lk = is_del ? S.var_length : L.nondel_L;
+    if (!F.ok || (is_del && Lk < 0)) {
+        w.altA_lo = w.altA_w1 = w.altB_lo = w.altB_w1 = 0u;
+        w.FL = 0u; w.FL1 = 0u; w.Lk = kTrapLk; w.hpk = zero_addr;      /* len 0: both keys clamp onto the zero word */
+        return w;
+    }
+    const int o1 = (S.meta >> 2) & 1, o2 = (S.meta >> 3) & 1;
+    const bool en = !(is_del && (S.dAB < L.ceil2sd));       /* singlesample.py:289,328 small deletions */
+    const int FL = L.FL;
+    const int LA = S.posA + S.ciA0 - m, HA = S.posA + S.ciA1 - m;
+    const int LB = S.posB + S.ciB0 + m + 1, HB = S.posB + S.ciB1 + m + 1;
+    set_win(w.altA_lo, w.altA_w1, LA - (o1 ? 0 : FL), HA + (o1 ? FL : 0), en);
+    set_win(w.altB_lo, w.altB_w1, LB - (o2 ? 0 : FL), HB + (o2 ? FL : 0), en);
+    w.FL = (unsigned)FL;
+    w.FL1 = (en && FL >= 0) ? (unsigned)FL + 1u : 0u;
+    w.Lk = (!is_del && Lk < 0) ? 0x7fffffffu : (unsigned)Lk;
+    w.hpk = F.addr | ((unsigned)F.len << 18);
+    return w;
+}
+
+/* sso association of a fragment's extra rows (singlesample.py:254-259, :367-378): the note above FragOut */
+struct FoldOut { double s, p_ref, p_alt; int lead; };
+
+__device__ __noinline__ FoldOut fold_continuations(const int lane, const int n, const unsigned nm, const unsigned vm,
+                                                   const double va, const double vb, double s, const double p_ref,
+                                                   const double p_alt)
+{
+    const unsigned full = 0xffffffffu;
+    FoldOut o;
+    o.s = s; o.p_ref = p_ref; o.p_alt = p_alt;
+    const unsigned NN = vm & ~nm;                   /* rows that continue a fragment */
+    o.lead = nm ? __ffs(nm) - 1 : (n < 32 ? n : 32);
+    const bool nonnew = (NN >> lane) & 1u;
+    const bool inner = nonnew && lane >= o.lead;    /* continues a fragment that starts in this chunk */
+    const unsigned below = nm & ((1u << lane) - 1u);
+    const int dist = inner ? lane - (31 - __clz(below)) : 0;
+    const bool pe_too = __ballot_sync(full, inner && (p_ref != 0.0 || p_alt != 0.0)) != 0u;
+    for (int k = 1; k < 32; ++k) {
+        if (!__any_sync(full, dist >= k)) break;
+        const double up = __shfl_up_sync(full, o.s, 1);
+        if (dist == k) o.s = __dadd_rn(__dadd_rn(up, va), vb);
+        if (pe_too) {
+            const double ur = __shfl_up_sync(full, o.p_ref, 1), ua = __shfl_up_sync(full, o.p_alt, 1);
+            if (dist == k) { o.p_ref = __dadd_rn(ur, p_ref); o.p_alt = __dadd_rn(ua, p_alt); }
+        }
+    }
+    const bool has_next = lane + 1 < 32 && ((NN >> (lane + 1 < 32 ? lane + 1 : 31)) & 1u);
+    if (lane >= o.lead && has_next) {
+        o.s = 0.0;
+        if (pe_too) { o.p_ref = 0.0; o.p_alt = 0.0; }
+    }
+    return o;
+}
+
+/* splits that are not the FIRST of their fragment are folded into the first one's sub-totals, as in
+ * score_split_chunk(); .p_ref / .p_alt of the result carry alt_seq / alt_clip */
+__device__ __noinline__ FoldOut fold_splits(const int lane, const int n, const unsigned nm, const double vs0,
+                                            const double vc0)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned vm = n >= 32 ? full : ((1u << n) - 1u);
+    FoldOut o;
+    o.s = 0.0; o.p_ref = vs0; o.p_alt = vc0;
+    const unsigned NN = vm & ~nm;
+    o.lead = nm ? __ffs(nm) - 1 : (n < 32 ? n : 32);
+    const bool nonnew = (NN >> lane) & 1u;
+    const bool inner = nonnew && lane >= o.lead;
+    const unsigned below = nm & ((1u << lane) - 1u);
+    const int dist = inner ? lane - (31 - __clz(below)) : 0;
+    for (int k = 1; k < 32; ++k) {
+        if (!__any_sync(full, dist >= k)) break;
+        const double us = __shfl_up_sync(full, o.p_ref, 1), uc = __shfl_up_sync(full, o.p_alt, 1);
+        if (dist == k) { o.p_ref = __dadd_rn(us, vs0); o.p_alt = __dadd_rn(uc, vc0); }
+    }
+    const bool has_next = lane + 1 < 32 && ((NN >> (lane + 1 < 32 ? lane + 1 : 31)) & 1u);
+    if (lane >= o.lead && has_next) { o.p_ref = 0.0; o.p_alt = 0.0; }
+    return o;
+}
+
+
 
 /* compact schema constants (svtyper_b200/compact.py) */
 enum : unsigned {
@@ -354,7 +524,7 @@ __device__ __forceinline__ void crow_stage2(const SvgtParams &p, const Tables &t
 }
 
 /* stage 3: the addends (singlesample.py:254-259: a = pm[A] if read A covers a breakend; :305-350: p_alt, p_ref),
- * continuation rows folded into their fragment's last row of the chunk (see score_frag_chunk()) */
+ * continuation rows folded into their fragment's last row of the chunk (see the note above FragOut) */
 template <int ASSOC>
 __device__ __forceinline__ FragOut crow_stage3(const int lane, const int n, const int4 r, const CRow &st)
 {

@@ -15,20 +15,12 @@
 #define SVGT_SMEM_HIST_WORDS 6144   /* 24 KB of insert-size histogram in smem      */
 #define SVGT_STAGE_ROWS 4           /* rows per lane per staged step (bulk path)   */
 
-/* kernel variants (svgt_set_variant / SVGT_VARIANT env): how fragment rows reach a lane */
+/* variants of the WIDE-row compatibility kernel (svgt_set_variant / SVGT_VARIANT env): how fragment rows reach a lane */
 enum {
     SVGT_VAR_DIRECT = 0,   /* per-lane LDG.128 x2 with register prefetch            */
     SVGT_VAR_BULK = 1,     /* per-lane cp.async.bulk (TMA 1-D) ring in shared memory */
-    SVGT_VAR_COOP = 2,     /* warp-cooperative, 8 sites interleaved per warp (svgt_coop.cu) */
-    SVGT_VAR_COOP4 = 3,    /* warp-cooperative, 4 sites interleaved per warp                 */
-    SVGT_VAR_RING = 4,     /* warp-cooperative, rows through a cp.async.bulk smem ring (svgt_ring.cu) */
-    SVGT_VAR_LEAN = 5,     /* warp-cooperative with the lean row scorer (svgt_lean.cu), the default:
-                              8 sites per work unit after a 1-2-4 ramp over the heaviest sites            */
-    SVGT_VAR_LEAN8 = 6,    /* the same, always 8 sites per unit (tests)                                     */
-    SVGT_VAR_LEAN2 = 7,    /* the same, always 2 sites per unit (tests)                                     */
-    SVGT_VAR_COUNT = 8
+    SVGT_VAR_COUNT = 2
 };
-#define SVGT_COOP_THREADS 256       /* 8 warps per CTA in the cooperative kernel     */
 
 struct SvgtParams {
     const int4 *sites;  long long n_sites;
@@ -45,7 +37,7 @@ struct SvgtParams {
     int min_aligned, split_slop, assoc_mode;
     double split_weight, disc_weight;
     svgt_out_row_t *out;
-    int *status;          /* [0] first error, [1] tile cursor, [2] error count, [3] spare */
+    int *status;          /* [0] first error, [1] work cursor, [2] error count, [3] finished-CTA count */
     int n_tiles;
     int hist_in_smem;
 };
@@ -65,9 +57,4 @@ struct SvgtCompactParams {
 /* Returns a cudaError_t as int.  `grid` <= 0 lets the launcher size a persistent grid. */
 int svgt_launch_score(const SvgtParams &p, int variant, cudaStream_t stream);
 size_t svgt_score_smem_bytes(const SvgtParams &p, int variant);
-int svgt_launch_coop(const SvgtParams &p, int variant, cudaStream_t stream);
-int svgt_launch_call(const SvgtParams &p, cudaStream_t stream);
-int svgt_launch_ring(const SvgtParams &p, cudaStream_t stream);
-int svgt_launch_lean(const SvgtParams &p, int variant, cudaStream_t stream);
-int svgt_lean_launches(void);
 int svgt_launch_compact(const SvgtCompactParams &cp, int unit_mode, cudaStream_t stream);

@@ -924,4 +924,237 @@ int svgt_pack_rows(const svgt_bam_t *bam, const int32_t **frags, int64_t *n_frag
     return SVGT_PACK_OK;
 }
 
+
+/* ------------------------------------------------------------------------------------------------ */
+/* wide rows -> compact rows (svtyper_b200/compact.py is the specification and the parity checker)   */
+/* ------------------------------------------------------------------------------------------------ */
+}  /* extern "C" */
+namespace {
+enum : uint32_t {
+    CW_CLS_A_ON_A = 1u << 28, CW_CLS_A_ON_B = 1u << 29, CW_CLS_B_ON_A = 1u << 30, CW_CLS_B_ON_B = 1u << 31,
+    CW_PAIRED = 1u << 25, CW_REV_A = 1u << 26, CW_REV_B = 1u << 27, CW_CONT = 1u << 28, CW_MULTI_A = 1u << 30,
+    CW_MULTI_B = 1u << 31, CW_SOFT = 1u << 16, CW_FIRST = 1u << 17, CW_WIDE = 1u << 18, CW_XEND = 1u << 19
+};
+const int CW_LEN_BITS = 14, CW_LEN_MAX = (1 << 14) - 1, CW_LIB_MAX = 511, CW_SLEN_MAX = 0xFFFF;
+
+inline int64_t wide_off(const int32_t *s, int lo) { return (int64_t)(uint32_t)s[lo] | ((int64_t)s[lo + 1] << 32); }
+
+/* one gap-free interval [s, e) on `tid` against both is_ref_seq windows (the oracle's ref_seq_hit()) */
+inline bool interval_hit(int32_t tid, int64_t s, int64_t e, const int32_t *site, int m)
+{
+    const int64_t pA = site[0], pB = site[1];
+    return (tid == site[6] && pA - m >= 0 && s <= pA - m && e >= pA + m) ||
+           (tid == site[7] && pB - m >= 0 && s <= pB - m && e >= pB + m);
+}
+
+/* rows the compact form of one site needs; fills them when `out` is given */
+struct SiteRows { int64_t nf, ns; };
+int compact_site(const int32_t *site, const int32_t *frags, int64_t n_frag, const int32_t *splits, int64_t n_split, int m,
+                 int32_t *out, SiteRows &cnt)
+{
+    cnt.nf = cnt.ns = 0;
+    if (site[9] & 16) return 0;                          /* SKIP: no rows the path may look at */
+    const int64_t foff = wide_off(site, 10), soff = wide_off(site, 13);
+    const int64_t nf = site[12], ns = site[15];
+    if (nf < 0 || ns < 0 || foff < 0 || soff < 0 || foff + nf > n_frag || soff + ns > n_split) return -1;
+    int32_t *o = out;
+    bool pendA = false, pendB = false;
+    for (int64_t j = 0; j < nf; ++j) {
+        const int32_t *f = frags + (foff + j) * 8;
+        const int fl = f[7];
+        const bool hasA = fl & F_HAS_A, hasB = fl & F_HAS_B, paired = fl & F_PAIRED;
+        if (fl & F_EXTRA) {
+            if (hasA && interval_hit(f[4], f[0], f[1], site, m)) pendA = true;
+            if (hasB && interval_hit(f[5], f[2], f[3], site, m)) pendB = true;
+            continue;
+        }
+        if (!hasA || (paired && !hasB)) return -2;
+        const uint32_t lib = ((uint32_t)f[6] >> 16) & 0xFFFFu;
+        if (lib > (uint32_t)CW_LIB_MAX) return -3;
+        if (out) {
+            const int64_t lenA = (int64_t)f[1] - f[0], lenB = (int64_t)f[3] - f[2];
+            const bool mA = (fl & F_MULTI_A) || lenA < 0 || lenA > CW_LEN_MAX;
+            const bool mB = hasB && ((fl & F_MULTI_B) || lenB < 0 || lenB > CW_LEN_MAX);
+            const bool hitA = (fl & F_MULTI_A) ? pendA : interval_hit(f[4], f[0], f[1], site, m);
+            const bool hitB = (fl & F_MULTI_B) ? pendB : (hasB && interval_hit(f[5], f[2], f[3], site, m));
+            const uint32_t la = mA ? (hitA ? 1u : 0u) : (uint32_t)lenA;
+            const uint32_t lb = mB ? (hitB ? 1u : 0u) : (hasB ? (uint32_t)lenB : 0u);
+            uint32_t cls = (f[4] == site[6] ? CW_CLS_A_ON_A : 0u) | (f[4] == site[7] ? CW_CLS_A_ON_B : 0u);
+            if (hasB) cls |= (f[5] == site[6] ? CW_CLS_B_ON_A : 0u) | (f[5] == site[7] ? CW_CLS_B_ON_B : 0u);
+            uint32_t w3 = ((uint32_t)f[6] & 0xFFu) | (hasB ? ((uint32_t)f[6] & 0xFF00u) : 0u) | (lib << 16);
+            w3 |= (paired ? CW_PAIRED : 0u) | ((fl & F_REV_A) ? CW_REV_A : 0u) | ((fl & F_REV_B) ? CW_REV_B : 0u) |
+                  ((fl & F_CONT) ? CW_CONT : 0u) | (mA ? CW_MULTI_A : 0u) | (mB ? CW_MULTI_B : 0u);
+            o[0] = f[0]; o[1] = hasB ? f[3] : 0;
+            o[2] = (int32_t)(la | (lb << CW_LEN_BITS) | cls);
+            o[3] = (int32_t)w3;
+            o += 4;
+        }
+        pendA = pendB = false;
+        ++cnt.nf;
+    }
+    for (int64_t j = 0; j < ns; ++j) {
+        const int32_t *q = splits + (soff + j) * 8;
+        const int64_t lenL = (int64_t)q[2] - q[1], lenR = (int64_t)q[5] - q[4];
+        const bool wide = lenL < 0 || lenL > CW_SLEN_MAX || lenR < 0 || lenR > CW_SLEN_MAX;
+        if (wide && cnt.ns % 32 == 31) {                 /* a WIDE row never sits in the last slot of a chunk */
+            if (out) { o[0] = o[1] = o[2] = o[3] = 0; o += 4; }
+            ++cnt.ns;
+        }
+        if (out) {
+            const uint32_t sfl = ((uint32_t)q[6] >> 16) & 0xFFFFu;
+            const uint32_t cls = (q[0] == site[6] ? 1u << 28 : 0u) | (q[0] == site[7] ? 1u << 29 : 0u) |
+                                 (q[3] == site[6] ? 1u << 30 : 0u) | (q[3] == site[7] ? 1u << 31 : 0u);
+            o[0] = q[1]; o[1] = q[4];
+            o[2] = wide ? 0 : (int32_t)((uint32_t)lenL | ((uint32_t)lenR << 16));
+            o[3] = (int32_t)(((uint32_t)q[6] & 0xFFFFu) | ((sfl & S_SOFT_CLIP) ? CW_SOFT : 0u) | ((sfl & S_FIRST) ? CW_FIRST : 0u) |
+                             (wide ? CW_WIDE : 0u) | cls);
+            o += 4;
+        }
+        ++cnt.ns;
+        if (wide) {
+            if (out) { o[0] = q[2]; o[1] = q[5]; o[2] = 0; o[3] = (int32_t)CW_XEND; o += 4; }
+            ++cnt.ns;
+        }
+    }
+    return 0;
+}
+
+template <typename Fn>
+void parallel_for(int64_t n, int n_threads, Fn fn)
+{
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    const int64_t block = 2048;
+    if (n_threads == 1 || n <= block) { fn(0, n); return; }
+    std::atomic<int64_t> next(0);
+    std::vector<std::thread> th;
+    auto work = [&]() {
+        for (;;) {
+            const int64_t lo = next.fetch_add(block);
+            if (lo >= n) break;
+            fn(lo, std::min(n, lo + block));
+        }
+    };
+    for (int t = 0; t < n_threads - 1; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+}  // namespace
+
+extern "C" {
+
+int svgt_compact_count(const int32_t *sites, int64_t n_sites, const int32_t *frags, int64_t n_frag, const int32_t *splits,
+                       int64_t n_split, int32_t min_aligned, int32_t n_threads, int64_t *row_off, int32_t *counts)
+{
+    if (n_sites < 0 || (n_sites > 0 && (!sites || !row_off || !counts))) return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    std::atomic<int> err(0);
+    parallel_for(n_sites, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            SiteRows c;
+            const int rc = compact_site(sites + i * 16, frags, n_frag, splits, n_split, min_aligned, nullptr, c);
+            if (rc) err = rc;
+            counts[2 * i] = (int32_t)c.nf; counts[2 * i + 1] = (int32_t)c.ns;
+        }
+    });
+    if (err == -3) return fail(SVGT_PACK_ERR_ARG, "compact schema holds library indices up to %d", CW_LIB_MAX);
+    if (err) return fail(SVGT_PACK_ERR_ARG, "malformed wide batch (row offsets out of range, or a fragment row without read A / a PAIRED row without read B)");
+    int64_t off = 0;
+    for (int64_t i = 0; i < n_sites; ++i) { row_off[i] = off; off += (int64_t)counts[2 * i] + counts[2 * i + 1]; }
+    row_off[n_sites] = off;
+    return SVGT_PACK_OK;
+}
+
+int svgt_compact_fill(const int32_t *sites, int64_t n_sites, const int32_t *frags, int64_t n_frag, const int32_t *splits,
+                      int64_t n_split, int32_t min_aligned, int32_t n_threads, const int64_t *row_off, const int32_t *counts,
+                      int32_t *out_sites, int32_t *out_rows)
+{
+    if (n_sites < 0 || (n_sites > 0 && (!sites || !row_off || !counts || !out_sites))) return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    if (n_sites > 0 && row_off[n_sites] > 0 && !out_rows) return fail(SVGT_PACK_ERR_ARG, "null row buffer");
+    std::atomic<int> err(0);
+    parallel_for(n_sites, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const int32_t *s = sites + i * 16;
+            SiteRows c;
+            const int rc = compact_site(s, frags, n_frag, splits, n_split, min_aligned, out_rows + row_off[i] * 4, c);
+            if (rc || c.nf != counts[2 * i] || c.ns != counts[2 * i + 1]) err = -1;
+            int32_t *o = out_sites + i * 12;
+            for (int k = 0; k < 6; ++k) o[k] = s[k];
+            o[6] = s[8];
+            o[7] = (s[9] & 0x1F) | (s[6] == s[7] ? 32 : 0);
+            o[8] = (int32_t)((uint64_t)row_off[i] & 0xFFFFFFFFu); o[9] = (int32_t)((uint64_t)row_off[i] >> 32);
+            o[10] = counts[2 * i]; o[11] = counts[2 * i + 1];
+        }
+    });
+    if (err) return fail(SVGT_PACK_ERR_ARG, "wide batch changed between svgt_compact_count and svgt_compact_fill");
+    return SVGT_PACK_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* FORMAT text of scored rows (reference parsers.py:375-398, singlesample.py:406-473)                */
+/* ------------------------------------------------------------------------------------------------ */
+}  /* extern "C" */
+namespace {
+struct OutRow { double gl[3]; double sq; int32_t gt, gq, dp, ro, ao, qr, qa, rs, as_, asc, rp, ap; };
+enum { FK_GT, FK_GQ, FK_SQ, FK_GL, FK_DP, FK_RO, FK_AO, FK_QR, FK_QA, FK_RS, FK_AS, FK_ASC, FK_RP, FK_AP, FK_AB, FK_COUNT };
+
+/* one sample column; style 0 = every field, 1 = the blank row, 2 = "./." and '.' for every other field */
+size_t format_call(const OutRow &r, const int32_t *order, int n_fields, int style, char *o)
+{
+    char *p = o;
+    for (int k = 0; k < n_fields; ++k) {
+        if (k) *p++ = ':';
+        const int f = order[k];
+        if (style == 2) { if (f == FK_GT) { memcpy(p, "./.", 3); p += 3; } else *p++ = '.'; continue; }
+        if (style == 1) {
+            if (f == FK_GT) { memcpy(p, "./.", 3); p += 3; }
+            else if (f == FK_GQ || f == FK_SQ || f == FK_GL || f == FK_AB) *p++ = '.';
+            else *p++ = '0';
+            continue;
+        }
+        const bool called = r.gt >= 0;
+        switch (f) {
+        case FK_GT: memcpy(p, !called ? "./." : r.gt == 0 ? "0/0" : r.gt == 1 ? "0/1" : "1/1", 3); p += 3; break;
+        case FK_GQ: if (called) p += sprintf(p, "%d", r.gq); else *p++ = '.'; break;
+        case FK_SQ: if (called) p += sprintf(p, "%0.2f", r.sq); else *p++ = '.'; break;
+        case FK_GL: p += sprintf(p, "%.0f,%.0f,%.0f", r.gl[0], r.gl[1], r.gl[2]); break;
+        case FK_AB: {
+            const int64_t tot = (int64_t)r.qr + r.qa;
+            if (tot) p += sprintf(p, "%.2g", (double)r.qa / (double)tot); else *p++ = '.';
+            break;
+        }
+        default: {
+            const int32_t *ints = &r.gt;               /* gt gq dp ro ao qr qa rs as asc rp ap */
+            static const int slot[FK_COUNT] = {0, 1, -1, -1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, -1};
+            p += sprintf(p, "%d", ints[slot[f]]);
+        }
+        }
+    }
+    return (size_t)(p - o);
+}
+}  // namespace
+
+extern "C" {
+
+int svgt_format_calls(const void *rows, int64_t n, const int32_t *order, int32_t n_fields, const uint8_t *style,
+                      int32_t n_threads, char *out, int64_t stride, int32_t *lengths)
+{
+    if (n < 0 || n_fields < 1 || n_fields > FK_COUNT || !order || stride < 16 * FK_COUNT + 64 ||
+        (n > 0 && (!rows || !out || !lengths || !style)))
+        return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    for (int k = 0; k < n_fields; ++k)
+        if (order[k] < 0 || order[k] >= FK_COUNT) return fail(SVGT_PACK_ERR_ARG, "bad field id");
+    const OutRow *r = (const OutRow *)rows;
+    parallel_for(n, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) lengths[i] = (int32_t)format_call(r[i], order, n_fields, style[i], out + i * stride);
+    });
+    return SVGT_PACK_OK;
+}
+
+int svgt_format_quals(const double *qual, int64_t n, char *out, int64_t stride, int32_t *lengths)
+{
+    if (n < 0 || stride < 32 || (n > 0 && (!qual || !out || !lengths))) return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    for (int64_t i = 0; i < n; ++i) lengths[i] = (int32_t)snprintf(out + i * stride, (size_t)stride, "%0.2f", qual[i]);
+    return SVGT_PACK_OK;
+}
+
 }  // extern "C"

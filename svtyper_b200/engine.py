@@ -39,6 +39,30 @@ def _torch():
     return torch
 
 
+class PinnedArena(object):
+    """Reusable pinned (page-locked) host buffers, one per array name: `alloc(name, shape, dtype)` returns a numpy
+    view of the first prod(shape) int32 words, growing the buffer geometrically when a batch is larger than any
+    before.  The packers / converters write compact rows straight into it and svgt_ctx_score_host_compact copies
+    from it asynchronously at full PCIe rate (pageable memory would be staged by the driver, at about half)."""
+
+    def __init__(self):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pinned host memory needs a CUDA device")
+        self._torch = torch
+        self._bufs = {}
+
+    def alloc(self, name, shape, dtype):
+        if np.dtype(dtype) != np.int32:
+            return np.empty(shape, dtype=dtype)
+        n = int(np.prod(shape)) if len(shape) else 1
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n:
+            t = self._torch.empty(max(n + n // 2, 1024), dtype=self._torch.int32, pin_memory=True)
+            self._bufs[name] = t
+        return t.numpy()[:n].reshape(shape)
+
+
 class DeviceBatch(object):
     """An EvidenceBatch resident in HBM plus its svgt_batch_t descriptor."""
 

@@ -17,8 +17,8 @@ OK, ERR_ARG, ERR_CUDA, ERR_LOG_TABLE, ERR_LIB_INDEX, ERR_NO_DEVICE, ERR_RANGE = 
 ERR_NAMES = {ERR_ARG: "SVGT_ERR_ARG", ERR_CUDA: "SVGT_ERR_CUDA", ERR_LOG_TABLE: "SVGT_ERR_LOG_TABLE",
              ERR_LIB_INDEX: "SVGT_ERR_LIB_INDEX", ERR_NO_DEVICE: "SVGT_ERR_NO_DEVICE",
              ERR_RANGE: "SVGT_ERR_RANGE"}
-VAR_DIRECT, VAR_BULK, VAR_COOP, VAR_COOP4, VAR_RING = 0, 1, 2, 3, 4
-VARIANTS = (0, 1, 2, 3, 4, 5, 6, 7)
+VAR_DIRECT, VAR_BULK = 0, 1
+VARIANTS = (0, 1)            # wide-row cross-check kernels; the default path is the compact one
 
 # every symbol include/svgt.h declares (tests check the library exports all of them)
 SYMBOLS = ("svgt_abi_version", "svgt_last_error", "svgt_device_count", "svgt_score_batch",

@@ -53,13 +53,57 @@ class LibScan(ctypes.Structure):
                 ("records_seen", ctypes.c_int64), ("n_hist", ctypes.c_int64)]
 
 
+def _stale():
+    return (not os.path.exists(LIB_PATH) or
+            any(os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in (SRC, HEADER)))
+
+
 def build(force=False):
-    """g++ -> svtyper_b200/libsvgt_pack.so (host code only, links zlib)."""
-    stale = (not os.path.exists(LIB_PATH) or
-             any(os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in (SRC, HEADER)))
-    if force or stale:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", LIB_PATH, SRC, "-lz", "-lpthread"])
+    """g++ -> svtyper_b200/libsvgt_pack.so (host code only, links zlib).
+
+    Normally run once by `__graft_entry__.build()` / at install time.  When a process finds the library
+    missing or older than its source it rebuilds it here, safely for concurrent callers (torchrun ranks,
+    worker processes): the compiler writes a private temporary file that is renamed over the target in one
+    step, under an exclusive lock, so nobody ever maps a half-written library."""
+    if not (force or _stale()):
+        return LIB_PATH
+    import fcntl
+    import tempfile
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():                      # somebody else may have built it while we waited
+                fd, tmp = tempfile.mkstemp(prefix=".libsvgt_pack.", suffix=".so", dir=HERE)
+                os.close(fd)
+                try:
+                    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", tmp, SRC,
+                                           "-lz", "-lpthread"])
+                    os.replace(tmp, LIB_PATH)
+                finally:
+                    if os.path.exists(tmp):
+                        os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
+
+
+_lib_error = None
+
+
+def available():
+    """True when libsvgt_pack.so can be built / loaded here (g++, zlib headers, a writable package directory
+    or a prebuilt library); otherwise the Python gather path serves the request."""
+    global _lib_error
+    if _lib is not None:
+        return True
+    if _lib_error is not None:
+        return False
+    try:
+        lib()
+        return True
+    except (OSError, subprocess.CalledProcessError, PermissionError) as e:
+        _lib_error = e
+        return False
 
 
 def lib():
@@ -97,6 +141,20 @@ def lib():
         L.svgt_pack_rows.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
                                      ctypes.POINTER(ctypes.c_int64)]
+        L.svgt_compact_count.restype = ctypes.c_int
+        L.svgt_compact_count.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        L.svgt_compact_fill.restype = ctypes.c_int
+        L.svgt_compact_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]
+        L.svgt_format_calls.restype = ctypes.c_int
+        L.svgt_format_calls.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.svgt_format_quals.restype = ctypes.c_int
+        L.svgt_format_quals.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        if L.svgt_pack_abi_version() != 2:
+            raise OSError("libsvgt_pack.so ABI %d != expected 2 (stale build?)" % L.svgt_pack_abi_version())
         _lib = L
     return _lib
 
@@ -165,7 +223,9 @@ def usable_path(bam):
     path = _path_of(bam)
     if not path.endswith(".bam") or not os.path.exists(path):
         return False
-    return os.path.exists(path + ".bai") or os.path.exists(os.path.splitext(path)[0] + ".bai")
+    if not (os.path.exists(path + ".bai") or os.path.exists(os.path.splitext(path)[0] + ".bai")):
+        return False
+    return available()
 
 
 def usable(sample):
@@ -222,18 +282,17 @@ def fetch_windows(sample, breakpoint, z, mode, flank=None):
 
 def pack_sample(sample, plan, mode, max_reads, z=3, threads=0):
     """Native gather + pack of every planned site of one sample -> EvidenceBatch."""
-    path = sample.bam.filename.decode() if isinstance(sample.bam.filename, bytes) else str(sample.bam.filename)
-    nb = NativeBam(path)
-    try:
-        flank = sample.fetch_flank(z)                       # one value per sample: max(mean + z * sd) over its libraries
-        sites = [fetch_windows(sample, bp, z, mode, flank) for bp in plan.breakpoints]
-        rg_names = list(sample.rg_to_lib.keys())
-        rg_lib = [sample.rg_to_lib[r] for r in rg_names]
-        n_lib = len(sample.libraries)
-        active = [i in sample.active for i in range(n_lib)]
-        cnt, frags, splits = nb.pack(sites, rg_names, rg_lib, active, mode, max_reads, threads)
-    finally:
-        nb.close()
+    nb = getattr(sample, "native_bam", None)               # one native handle (header + index) per sample, reused
+    if nb is None:                                          # by every chunk of the VCF; SampleInfo.close() closes it
+        path = sample.bam.filename.decode() if isinstance(sample.bam.filename, bytes) else str(sample.bam.filename)
+        nb = sample.native_bam = NativeBam(path)
+    flank = sample.fetch_flank(z)                           # one value per sample: max(mean + z * sd) over its libraries
+    sites = [fetch_windows(sample, bp, z, mode, flank) for bp in plan.breakpoints]
+    rg_names = list(sample.rg_to_lib.keys())
+    rg_lib = [sample.rg_to_lib[r] for r in rg_names]
+    n_lib = len(sample.libraries)
+    active = [i in sample.active for i in range(n_lib)]
+    cnt, frags, splits = nb.pack(sites, rg_names, rg_lib, active, mode, max_reads, threads)
     rows = np.zeros((len(plan.breakpoints), ev.SITE_WORDS), dtype=np.int64)
     f_off = s_off = 0
     for i, bp in enumerate(plan.breakpoints):
@@ -254,3 +313,70 @@ def pack_sample(sample, plan, mode, max_reads, z=3, threads=0):
     batch = ev.EvidenceBatch(rows.astype(np.int32), frags, splits, sample.library_table())
     batch.order = batch.length_order()
     return batch
+
+
+# ---------------------------------------------------------------------------------------------
+# wide -> compact rows and FORMAT text, natively (the numpy / Python forms are their parity checkers)
+def compact_from_wide(batch, min_aligned=20, alloc=None, threads=0):
+    """compact.compact_from_wide() in C (threaded over sites); `alloc(name, shape, dtype)` may supply the
+    destination arrays, e.g. pinned host memory the engine copies from directly."""
+    from . import compact as cp
+    alloc = alloc or (lambda name, shape, dtype: np.empty(shape, dtype=dtype))
+    n = batch.n_sites
+    sites = np.ascontiguousarray(batch.sites, dtype=np.int32)
+    frags = np.ascontiguousarray(batch.frags, dtype=np.int32)
+    splits = np.ascontiguousarray(batch.splits, dtype=np.int32)
+    row_off = np.zeros(n + 1, dtype=np.int64)
+    counts = np.zeros((max(n, 1), 2), dtype=np.int32)
+    _check(lib().svgt_compact_count(sites.ctypes.data, n, frags.ctypes.data, batch.n_frag, splits.ctypes.data, batch.n_split,
+                                    int(min_aligned), int(threads), row_off.ctypes.data, counts.ctypes.data))
+    out_sites = alloc("sites", (n, cp.CSITE_WORDS), np.int32)
+    out_rows = alloc("rows", (int(row_off[n]), cp.CROW_WORDS), np.int32)
+    _check(lib().svgt_compact_fill(sites.ctypes.data, n, frags.ctypes.data, batch.n_frag, splits.ctypes.data, batch.n_split,
+                                   int(min_aligned), int(threads), row_off.ctypes.data, counts.ctypes.data,
+                                   out_sites.ctypes.data, out_rows.ctypes.data if out_rows.size else None))
+    out = cp.CompactBatch.__new__(cp.CompactBatch)
+    out.sites, out.rows, out.libs, out.order, out.min_aligned = out_sites, out_rows, batch.libs, None, int(min_aligned)
+    if batch.order is not None:
+        order = alloc("order", (n,), np.int32)
+        order[:] = out.length_order()
+        out.order = order
+    return out
+
+
+FIELD_IDS = {k: i for i, k in enumerate(("GT", "GQ", "SQ", "GL", "DP", "RO", "AO", "QR", "QA", "RS", "AS", "ASC", "RP", "AP", "AB"))}
+STYLE_FULL, STYLE_BLANK, STYLE_DOTS = 0, 1, 2
+
+
+def format_calls(rows, order, style, threads=0):
+    """Sample-column text of scored OUT_DTYPE rows: list of str, one per row (see include/svgt_pack.h)."""
+    n = int(rows.shape[0])
+    if n == 0:
+        return []
+    rows = np.ascontiguousarray(rows)
+    ids = np.array([FIELD_IDS[k] for k in order], dtype=np.int32)
+    style = np.ascontiguousarray(style, dtype=np.uint8)
+    stride = 16 * 15 + 64 + 96
+    buf = np.empty(n * stride, dtype=np.uint8)
+    lens = np.empty(n, dtype=np.int32)
+    _check(lib().svgt_format_calls(rows.ctypes.data, n, ids.ctypes.data, len(ids), style.ctypes.data, int(threads),
+                                   buf.ctypes.data, stride, lens.ctypes.data))
+    raw = buf.tobytes()
+    return [raw[i * stride:i * stride + l].decode("ascii") for i, l in enumerate(lens.tolist())]
+
+
+def format_quals(qual):
+    """'%0.2f' of every value, as a list of str."""
+    q = np.ascontiguousarray(qual, dtype=np.float64)
+    n = int(q.shape[0])
+    if n == 0:
+        return []
+    stride = 32
+    big = np.abs(q) >= 1e20
+    if big.any() or not np.isfinite(q).all():
+        return ["%0.2f" % v for v in q.tolist()]
+    buf = np.empty(n * stride, dtype=np.uint8)
+    lens = np.empty(n, dtype=np.int32)
+    _check(lib().svgt_format_quals(q.ctypes.data, n, buf.ctypes.data, stride, lens.ctypes.data))
+    raw = buf.tobytes()
+    return [raw[i * stride:i * stride + l].decode("ascii") for i, l in enumerate(lens.tolist())]

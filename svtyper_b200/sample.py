@@ -244,6 +244,10 @@ class SampleInfo(object):
                             ("mapped", self.mapped), ("unmapped", self.unmapped)])
 
     def close(self):
+        nb = getattr(self, "native_bam", None)
+        if nb is not None:
+            nb.close()
+            self.native_bam = None
         self.bam.close()
 
 

@@ -46,3 +46,16 @@ def fixture_npz():
 def fixture_batch(fixture_npz):
     from util import batch_from_npz
     return batch_from_npz(fixture_npz)
+
+
+@pytest.fixture()
+def oracle_scorer(oracle, monkeypatch):
+    """CPU tests of the host plumbing: the parity oracle stands in for the CUDA engine.  It is installed by
+    monkeypatching genotype.score (the product module has no injection seam) and reads the product's COMPACT
+    batches through compact.wide_from_compact, so the encoding is exercised too."""
+    from svtyper_b200 import compact as cp, genotype
+
+    def scorer(batch, **params):
+        return oracle.score(cp.wide_from_compact(batch), **params)
+    monkeypatch.setattr(genotype, "score", scorer)
+    yield scorer

@@ -51,23 +51,51 @@ def test_header_is_plain_c_and_layout_matches_ctypes(tmp_path):
     assert vals[2:] == [getattr(native.SvgtBatch, f).offset for f in fields]
 
 
+def test_compact_struct_layout_matches_ctypes(tmp_path):
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields = [f[0] for f in native.SvgtCBatch._fields_]
+    body = "".join('printf("%%zu\\n", offsetof(svgt_cbatch_t, %s));' % f for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "svgt.h"\n'
+                   'int main(void){printf("%zu\\n", sizeof(svgt_cbatch_t));' + body + 'return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"),
+                           str(src), "-o", str(exe)])
+    vals = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == ctypes.sizeof(native.SvgtCBatch)
+    assert vals[1:] == [getattr(native.SvgtCBatch, f).offset for f in fields]
+
+
 def test_null_batch_is_an_argument_error(lib):
     rc = lib.svgt_score_batch(None, None, None, None)
     assert rc == native.ERR_ARG
     assert b"null" in lib.svgt_last_error()
     assert lib.svgt_launches_per_batch(None) == native.ERR_ARG
+    assert lib.svgt_score_compact(None, None, None, None) == native.ERR_ARG
+    assert lib.svgt_ctx_score_host_compact(None, None, None) == native.ERR_ARG
+
+
+def test_compact_argument_checks(lib):
+    """Host-side validation of a compact batch needs no GPU: min_aligned the rows were packed for, unit_mode."""
+    import numpy as np
+    b = native.SvgtCBatch()
+    z = np.zeros(64, dtype=np.float64)
+    b.pm = b.logt = b.consts = z.ctypes.data
+    b.n_log = 8
+    b.min_aligned, b.rows_min_aligned = 20, 25
+    assert lib.svgt_score_compact(ctypes.byref(b), None, None, None) == native.ERR_ARG
+    assert b"min_aligned" in lib.svgt_last_error()
+    b.rows_min_aligned = 20
+    b.unit_mode = 7
+    assert lib.svgt_score_compact(ctypes.byref(b), None, None, None) == native.ERR_ARG
 
 
 def test_set_variant(lib):
     assert lib.svgt_set_variant(1) == 1
     assert lib.svgt_set_variant(0) == 0
     assert lib.svgt_set_variant(99) == native.ERR_ARG
-    assert lib.svgt_set_variant(2) == 2
-    assert lib.svgt_set_variant(3) == 3
-    assert lib.svgt_set_variant(4) == 4
-    assert lib.svgt_set_variant(5) == 5
-    assert lib.svgt_set_variant(7) == 7
-    assert lib.svgt_set_variant(-1) in (0, 1, 2, 3, 4, 5, 6, 7)
+    assert lib.svgt_set_variant(2) == native.ERR_ARG
+    assert lib.svgt_set_variant(-1) in (0, 1)
 
 
 def test_no_cpu_fallback(lib):

@@ -22,7 +22,6 @@ def _strip(path):
 
 
 def test_classic_sv_genotype_on_gpu(tmp_path):
-    genotype.set_scorer(None)
     out = tmp_path / "classic.vcf"
     with open(VCF) as fin, open(out, "w") as fout:
         classic.sv_genotype(BAM, fin, fout, 20, 1, 1, 1000000, LIB, False, None, None, False, None, 1e10)
@@ -31,7 +30,6 @@ def test_classic_sv_genotype_on_gpu(tmp_path):
 
 @pytest.mark.parametrize("cores", [None, 1])
 def test_sso_genotype_on_gpu(tmp_path, cores):
-    genotype.set_scorer(None)
     out = tmp_path / "sso.vcf"
     with open(VCF) as fin, open(out, "w") as fout:
         singlesample.sso_genotype(BAM, fin, fout, 20, 1, 1, 1000000, LIB, False, None, False, 1000, 1e10,

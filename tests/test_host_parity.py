@@ -26,12 +26,6 @@ def ref():
     return ref_loader.load()
 
 
-@pytest.fixture()
-def oracle_scorer(oracle):
-    genotype.set_scorer(lambda batch, **params: oracle.score(batch, **params))
-    yield
-    genotype.set_scorer(None)
-
 
 # ---- CIGAR helpers: the reference's own unit tests (tests/test_svtyper.py:14-56) -----------------
 def test_cigar_helpers_match_reference_unit_tests():
