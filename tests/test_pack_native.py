@@ -60,10 +60,12 @@ def sample():
 
 def test_abi_exports_every_declared_symbol():
     L = packer.lib()
-    assert L.svgt_pack_abi_version() == 1
+    assert L.svgt_pack_abi_version() == 2
     header = open(os.path.join(REPO, "include", "svgt_pack.h")).read()
-    names = set(re.findall(r"\b(svgt_(?:pack|bam)_[a-z_]+)\s*\(", header))
-    assert {"svgt_bam_open", "svgt_bam_close", "svgt_bam_count", "svgt_pack_sites", "svgt_pack_rows"} <= names
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(svgt_(?:pack|bam|compact|format)_[a-z_]+)\s*\(", header))
+    assert {"svgt_bam_open", "svgt_bam_close", "svgt_bam_count", "svgt_pack_sites", "svgt_pack_rows",
+            "svgt_compact_count", "svgt_compact_fill", "svgt_format_calls", "svgt_format_quals"} <= names
     for n in names:
         assert hasattr(L, n), n
 
@@ -316,3 +318,32 @@ print("survived")
 ''' % (REPO, BAM, str(tmp_path))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "survived" in r.stdout, (r.returncode, r.stderr[-500:])
+
+
+def test_native_compact_converter_and_formatter_match_python(oracle):
+    """libsvgt_pack.so's wide -> compact converter and FORMAT formatter against their Python specifications
+    (compact.compact_from_wide, genotype.ChunkWriter's Python fallback): identical bytes / text."""
+    from svtyper_b200 import compact as cp, synth
+    for cfg, n, m in (("mixed100k", 6000, 20), ("stress1m", 2500, 20), ("del1m4lib", 4000, 7)):
+        b = synth.generate(cfg, n_sites=n, seed=3)
+        a = cp.compact_from_wide(b, min_aligned=m)
+        c = packer.compact_from_wide(b, min_aligned=m, threads=3)
+        assert np.array_equal(a.sites, c.sites) and np.array_equal(a.rows, c.rows) and np.array_equal(a.order, c.order)
+        assert c.min_aligned == m
+    bad = ev.EvidenceBatch(b.sites.copy(), b.frags.copy(), b.splits.copy(), b.libs)
+    bad.frags[:, 6] |= 600 << 16
+    with pytest.raises(packer.PackError):
+        packer.compact_from_wide(bad)
+    rows = oracle.score(synth.generate("stress1m", n_sites=3000, seed=5))
+    import io
+    header = vcf.VcfHeader().parse([])
+    header.ensure_svtyper_fields()
+    header.add_sample("S")
+    for classic_mode in (False, True):
+        w = genotype.ChunkWriter(header, ["S"], classic_mode)
+        fast, style = w._texts(rows)
+        w.native = None
+        slow, style2 = w._texts(rows)
+        assert fast == slow and np.array_equal(style, style2)
+    q = np.array([0.0, 0.005, 2.675, 1743.0030805692013, 99999.995, 1e-9])
+    assert packer.format_quals(q) == ["%0.2f" % v for v in q.tolist()]
