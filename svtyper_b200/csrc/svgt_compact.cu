@@ -36,10 +36,17 @@ namespace {
 #ifndef SVGT_C_MINB
 #define SVGT_C_MINB 1
 #endif
+#ifndef SVGT_C_PREFETCH
+#define SVGT_C_PREFETCH 0
+#endif
+#ifndef SVGT_C_UNROLL
+#define SVGT_C_UNROLL 1
+#endif
 #ifndef SVGT_C_DEPTH
 #define SVGT_C_DEPTH 2              /* super-step slots in the ring */
 #endif
 constexpr int kCD = SVGT_C_DEPTH;
+constexpr int kCUnroll = SVGT_C_UNROLL;
 constexpr int kCWarps = SVGT_C_THREADS / 32;
 constexpr int kCHistPad = 8;
 
@@ -366,11 +373,29 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                 if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
             };
             if (!sp) {
-#pragma unroll 1
+#if SVGT_C_PREFETCH
+                /* the next site's row is fetched while this one is scored (parking only touches this site's bytes) */
+                auto raw_row = [&](const int g) -> int4 {
+                    int4 r;
+                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                                 : "r"(slotaddr + (unsigned)g * 528u + (unsigned)lane * 16u));
+                    return r;
+                };
+                int4 rn = raw_row(0);
+#endif
+#pragma unroll kCUnroll
                 for (int g = 0; g < G; ++g) {
+#if SVGT_C_PREFETCH
+                    int4 r = rn;
+                    if (g + 1 < G) rn = raw_row(g + 1);
+                    const int n = cnts[g] - step * 32;
+                    if (n <= 0) continue;
+                    if (lane >= n) r = make_int4(0, 0, 0, 0);
+#else
                     const int n = cnts[g] - step * 32;
                     if (n <= 0) continue;
                     const int4 r = load_row(g, n);
+#endif
                     __syncwarp();
                     const CSiteF &F = ws.sf[g];
                     CRow a;

@@ -165,7 +165,7 @@ class LibraryInfo(object):
 class SampleInfo(object):
     """One BAM: its sample name, libraries (in table order) and read-group map."""
 
-    def __init__(self, name, bam, libraries, mapped, unmapped):
+    def __init__(self, name, bam, libraries, mapped, unmapped, shadowed=()):
         self.name, self.bam = name, bam
         self.libraries = libraries
         self.mapped, self.unmapped = mapped, unmapped
@@ -173,7 +173,16 @@ class SampleInfo(object):
         for i, lib in enumerate(libraries):
             for rg in lib.readgroups:
                 self.rg_to_lib[rg] = i
-        self.active = set(i for i, lib in enumerate(libraries) if lib.prevalence >= MIN_LIB_PREVALENCE)
+        # `shadowed`: entries of a -l JSON whose library name is listed again later.  The reference keys its
+        # library dict by name (parsers.py:636), so the later entry replaces the earlier one there, while the
+        # earlier one's read groups keep pointing at the replaced object (parsers.py:643-644): their reads are
+        # still scored with the earlier entry's statistics, are active iff the name is (the active list holds
+        # names: parsers.py:614-617, taken from the surviving entry), and the entry no longer counts for the
+        # fetch flank (parsers.py:689).
+        self.shadowed = set(shadowed)
+        last = {lib.name: lib for i, lib in enumerate(libraries) if i not in self.shadowed}
+        self.active = set(i for i, lib in enumerate(libraries)
+                          if last.get(lib.name, lib).prevalence >= MIN_LIB_PREVALENCE)
         self._table = None
 
     @classmethod
@@ -185,11 +194,11 @@ class SampleInfo(object):
         except KeyError:
             sys.stderr.write("Error: sample %s not found in JSON library file.\n" % name)
             sys.exit(1)
-        # a library name listed twice keeps its last definition (the reference keys a dict by name)
-        by_name = OrderedDict()
-        for lib in libs:
-            by_name[lib.name] = lib
-        return cls(name, bam, list(by_name.values()), entry["mapped"], entry["unmapped"])
+        last = {}
+        for i, lib in enumerate(libs):
+            last[lib.name] = i
+        shadowed = [i for i, lib in enumerate(libs) if last[lib.name] != i]
+        return cls(name, bam, libs, entry["mapped"], entry["unmapped"], shadowed=shadowed)
 
     @classmethod
     def from_bam(cls, bam, num_samp, native=None):
@@ -231,7 +240,7 @@ class SampleInfo(object):
         return cls.from_bam(bam, num_samp)
 
     def fetch_flank(self, z=3):
-        return max(lib.mean + lib.sd * z for lib in self.libraries)
+        return max(lib.mean + lib.sd * z for i, lib in enumerate(self.libraries) if i not in self.shadowed)
 
     def library_table(self):
         if self._table is None:

@@ -204,3 +204,29 @@ def test_sso_records_with_existing_format_values_match_reference(ref, oracle_sco
     got, want = _strip(open(mine).read()), _strip(open(theirs).read())
     assert got == want
     assert any(":XX" in l.split("\t")[8] for l in got if not l.startswith("#") and l)
+
+
+@needs_ref
+def test_duplicate_library_name_in_json_matches_reference(ref, oracle_scorer, tmp_path):
+    """A -l JSON that lists one library name twice: the reference's name-keyed dict keeps the later entry, the
+    earlier entry's read groups keep pointing at the replaced object and their reads are skipped
+    (parsers.py:636-644).  Same text here."""
+    doc = json.load(open(LIB))
+    name = list(doc.keys())[0]
+    first = doc[name]["libraryArray"][0]
+    second = dict(first)
+    second["readgroups"] = []
+    second["mean"], second["sd"] = first["mean"] + 40.0, first["sd"] + 5.0
+    doc[name]["libraryArray"] = [first, second]
+    lib = tmp_path / "dup.json"
+    lib.write_text(json.dumps(doc))
+    lines = open(VCF).read().split("\n")
+    path = tmp_path / "few.vcf"
+    path.write_text("\n".join([l for l in lines if l.startswith("#")] + [l for l in lines if l and not l.startswith("#")][:30]) + "\n")
+    args = (20, 1, 1, 1000000, str(lib), False, None, False, 1000, 1e10, None, 1000)
+    theirs, mine = tmp_path / "ref.vcf", tmp_path / "mine.vcf"
+    with open(path) as fin, open(theirs, "w") as fout:
+        ref.singlesample.sso_genotype(BAM, fin, fout, *args)
+    with open(path) as fin, open(mine, "w") as fout:
+        singlesample.sso_genotype(BAM, fin, fout, *args)
+    assert _strip(open(mine).read()) == _strip(open(theirs).read())
