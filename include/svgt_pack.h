@@ -132,6 +132,11 @@ int svgt_format_calls(const void *rows, int64_t n, const int32_t *order, int32_t
                       int32_t n_threads, char *out, int64_t stride, int32_t *lengths);
 int svgt_format_quals(const double *qual, int64_t n, char *out, int64_t stride, int32_t *lengths);
 
+/* GT / GQ / SQ of `n` scored rows recomputed in place from their GL values with the host libm, the way CPython
+ * evaluates singlesample.py:447-471 (the device's pow / log are not correctly rounded; GL and every count are
+ * bit-exact already). */
+int svgt_host_sq(void *rows, int64_t n, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@
 #include "../../include/svgt_pack.h"
 
 #include <zlib.h>
+#include <math.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -1146,6 +1147,42 @@ int svgt_format_calls(const void *rows, int64_t n, const int32_t *order, int32_t
     const OutRow *r = (const OutRow *)rows;
     parallel_for(n, n_threads, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) lengths[i] = (int32_t)format_call(r[i], order, n_fields, style[i], out + i * stride);
+    });
+    return SVGT_PACK_OK;
+}
+
+/* SQ / GQ / GT from the (bit-exact) GL values with the HOST libm, exactly as CPython evaluates
+ * singlesample.py:447-471: gt_sum = sum(10 ** gl), SQ = abs(-10 * (gl[0] - math.log(gt_sum, 10))); all three 10 ** gl
+ * underflowing to 0.0 gives the "./." row.  The device computes the same with CUDA's pow / log, which are not
+ * correctly rounded: this pass makes the printed SQ and QUAL independent of that. */
+int svgt_host_sq(void *rows, int64_t n, int32_t n_threads)
+{
+    if (n < 0 || (n > 0 && !rows)) return fail(SVGT_PACK_ERR_ARG, "bad argument");
+    OutRow *r = (OutRow *)rows;
+    parallel_for(n, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            OutRow &o = r[i];
+            if (o.gt < -1) continue;                     /* blank / skipped rows carry no likelihoods */
+            double gt_sum = 0.0;
+            for (int g = 0; g < 3; ++g) gt_sum += pow(10.0, o.gl[g]);
+            if (gt_sum > 0) {
+                int best = 0;
+                for (int g = 1; g < 3; ++g) if (o.gl[g] > o.gl[best]) best = g;
+                int second = -1;
+                for (int g = 0; g < 3; ++g) {
+                    if (g == best) continue;
+                    if (second < 0 || o.gl[g] > o.gl[second]) second = g;
+                }
+                const double gt_sum_log = log(gt_sum) / log(10.0);
+                o.sq = fabs(-10 * (o.gl[0] - gt_sum_log));
+                double phred = -10 * (o.gl[second] - o.gl[best]);
+                if (phred > 200) phred = 200;
+                o.gq = (int32_t)phred;
+                o.gt = best;
+            } else {
+                o.gq = -1; o.sq = 0.0; o.gt = -1;
+            }
+        }
     });
     return SVGT_PACK_OK;
 }

@@ -368,6 +368,8 @@ def run_pipeline(samples, plans, write_lines, gather, mode, classic, min_aligned
             merged = merge_samples(packed, alloc=allocs[k & 1])
             rows = score(merged, min_aligned=min_aligned, split_slop=SPLIT_SLOP, split_weight=split_weight,
                          disc_weight=disc_weight, assoc_mode=assoc)
+            if writer.native is not None:                   # SQ (and so QUAL) from the bit-exact GL with the host libm
+                rows = writer.native.host_sq(np.ascontiguousarray(rows), threads=threads)
             for k, s in enumerate(samples):
                 rows_by_sample[s.name] = rows[k * n:(k + 1) * n]
         else:

@@ -151,6 +151,8 @@ def lib():
         L.svgt_format_calls.restype = ctypes.c_int
         L.svgt_format_calls.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                         ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.svgt_host_sq.restype = ctypes.c_int
+        L.svgt_host_sq.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32]
         L.svgt_format_quals.restype = ctypes.c_int
         L.svgt_format_quals.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         if L.svgt_pack_abi_version() != 2:
@@ -363,6 +365,14 @@ def format_calls(rows, order, style, threads=0):
                                    buf.ctypes.data, stride, lens.ctypes.data))
     raw = buf.tobytes()
     return [raw[i * stride:i * stride + l].decode("ascii") for i, l in enumerate(lens.tolist())]
+
+
+def host_sq(rows, threads=0):
+    """GT / GQ / SQ of scored OUT_DTYPE rows recomputed in place from GL with the host libm (see svgt_pack.h)."""
+    if rows.shape[0]:
+        assert rows.flags["C_CONTIGUOUS"] and rows.flags["WRITEABLE"]
+        _check(lib().svgt_host_sq(rows.ctypes.data, int(rows.shape[0]), int(threads)))
+    return rows
 
 
 def format_quals(qual):

@@ -63,7 +63,7 @@ def test_abi_exports_every_declared_symbol():
     assert L.svgt_pack_abi_version() == 2
     header = open(os.path.join(REPO, "include", "svgt_pack.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    names = set(re.findall(r"\b(svgt_(?:pack|bam|compact|format)_[a-z_]+)\s*\(", header))
+    names = set(re.findall(r"\b(svgt_(?:pack|bam|compact|format|host)_[a-z_]+)\s*\(", header))
     assert {"svgt_bam_open", "svgt_bam_close", "svgt_bam_count", "svgt_pack_sites", "svgt_pack_rows",
             "svgt_compact_count", "svgt_compact_fill", "svgt_format_calls", "svgt_format_quals"} <= names
     for n in names:
@@ -345,5 +345,15 @@ def test_native_compact_converter_and_formatter_match_python(oracle):
         w.native = None
         slow, style2 = w._texts(rows)
         assert fast == slow and np.array_equal(style, style2)
+    # host_sq: GT / GQ / SQ recomputed from GL with the host libm are the oracle's (same libm, same expressions),
+    # whatever the scorer left there
+    want = rows.copy()
+    junk = rows.copy()
+    called = junk["GT"] >= -1
+    junk["SQ"][called] *= 1.0000001
+    junk["GQ"][called] = 7
+    junk["GT"][called] = 1
+    packer.host_sq(junk, threads=2)
+    assert junk.tobytes() == want.tobytes()
     q = np.array([0.0, 0.005, 2.675, 1743.0030805692013, 99999.995, 1e-9])
     assert packer.format_quals(q) == ["%0.2f" % v for v in q.tolist()]
