@@ -13,10 +13,14 @@ it fits one GPU).  With N > 1 the run measures BOTH readings of "1 -> 8 B200 sit
   strong  ONE global batch of `--sites` breakpoints, cut into contiguous site ranges balanced by evidence
           rows (svtyper_b200/shard.py), rank r scoring range r.
 
-In both, the 80-byte output rows of every rank land in rank 0's buffer: each rank's call kernel stores its rows
-straight into that buffer over NVLink (CUDA IPC peer mapping, one flag per rank; no collective inside the
-step), or -- if peer mapping is unavailable -- through one NCCL gather per step.  `--scaling` picks which of
-the two is the line's `value` (default weak); the other is reported under its own key.  One JSON line on rank 0.
+In both, the 80-byte output rows of every rank land in a buffer rank 0 exports through CUDA IPC, with one flag
+word per rank and no collective inside the step (`--gather`, several may be listed, the first is the line's):
+  dma   (default) each rank's copy engine forwards a finished step's rows over NVLink on a side stream, under the
+        NEXT step's kernels; the flag follows the copy in stream order;
+  peer  the call kernel stores its rows straight into rank 0's buffer (the transfer then sits at the end of the step);
+  nccl  one NCCL gather per step, double-buffered (round 1's route; also the fallback when IPC mapping fails).
+`--scaling` picks which of weak / strong is the line's `value` (default weak); the other is reported under its own
+key.  One JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -51,7 +55,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="sites in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the site-sharded (strong) measurement")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--gather", default="dma", help="comma-separated list of dma | peer | nccl; the first is the line's")
     return ap.parse_args()
 
 
@@ -173,12 +177,10 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------
 class RowGather(object):
-    """Where every rank's output rows end up: rank 0's buffer.
+    """Where every rank's output rows end up: rank 0's buffer (see the module docstring for the three routes).
 
-    peer: rank 0 owns a CUDA-IPC-exported buffer (two halves, alternating by step) plus one flag word per rank;
-          every rank maps both and hands its call kernel `out_final` / `done_flag` pointers into them, so the rows
-          cross NVLink as plain stores and the step needs no collective -- rank 0 just waits for the flags.
-    nccl: one dist.gather of the padded shards per step (the fallback, and the checked alternative).
+    dma / peer: rank 0 owns a CUDA-IPC-exported buffer (two halves, alternating by step) plus one flag word per
+    rank; every rank maps both.  nccl: one dist.gather of the padded shards per step.
     """
 
     def __init__(self, mode, rank, world, counts, device):
@@ -190,9 +192,11 @@ class RowGather(object):
         self.total = sum(self.counts)
         self.mode = mode if world > 1 else "none"
         self.lib = native.lib()
+        self.torch = torch
         self.buf = self.flags = None
         self._owned = []
-        if self.mode == "peer":
+        self.err = None
+        if self.mode in ("peer", "dma"):
             ok = 1
             handles = [None, None]
             try:
@@ -223,6 +227,11 @@ class RowGather(object):
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             if int(t.item()) == 0:
                 self.mode = "nccl"
+        n_mine = self.counts[rank]
+        if self.mode == "dma":
+            self.outs = [torch.zeros((max(n_mine, 1), 80), dtype=torch.uint8, device=device) for _ in range(2)]
+            self.side = torch.cuda.Stream(device=device)
+            self.sent = [None, None]
         if self.mode == "nccl":
             pad = max(self.counts)
             self.pad = pad
@@ -231,35 +240,68 @@ class RowGather(object):
             self.pending = [None, None]
         self.step_no = 0
 
+    def _dst(self, half):
+        return self.buf + (half * self.total + self.offsets[self.rank]) * 80
+
     def arm(self, desc, half):
-        """Point this rank's launch descriptor at its slice of rank 0's buffer for the coming step."""
+        """Point this rank's launch descriptor at where the coming step's final rows go."""
         self.step_no += 1
         if self.mode == "peer":
-            desc.out_final = self.buf + (half * self.total + self.offsets[self.rank]) * 80
+            desc.out_final = self._dst(half)
             desc.done_flag = self.flags + 4 * self.rank
             desc.done_value = self.step_no
+        else:
+            desc.out_final = None
+            desc.done_flag = None
 
     def out_tensor(self, dev_out, half):
-        return self.send[half] if self.mode == "nccl" else dev_out
+        if self.mode == "nccl":
+            return self.send[half]
+        if self.mode == "dma":
+            return self.outs[half]
+        return dev_out
 
-    def after_score(self, stream, half):
-        import torch.distributed as dist
-        if self.mode == "peer" and self.rank == 0:
-            from svtyper_b200 import native
-            native.check(self.lib.svgt_wait_flags(ctypes.c_void_p(self.flags), self.world, self.step_no,
-                                                  ctypes.c_void_p(stream.cuda_stream)))
-        elif self.mode == "nccl":
-            self.pending[half] = dist.gather(self.send[half], self.recv[half], dst=0, async_op=True)
-
-    def before_score(self, half):
+    def before_score(self, stream, half):
         if self.mode == "nccl" and self.pending[half] is not None:
             self.pending[half].wait()
             self.pending[half] = None
+        if self.mode == "dma" and self.sent[half] is not None:
+            stream.wait_event(self.sent[half])          # the copy that read outs[half] two steps ago
+            self.sent[half] = None
 
-    def drain(self):
+    def after_score(self, stream, half):
+        import torch.distributed as dist
+        from svtyper_b200 import native
+        if self.mode == "peer" and self.rank == 0:
+            native.check(self.lib.svgt_wait_flags(ctypes.c_void_p(self.flags), self.world, self.step_no,
+                                                  ctypes.c_void_p(stream.cuda_stream)))
+        elif self.mode == "dma":
+            done = self.torch.cuda.Event()
+            done.record(stream)
+            self.side.wait_event(done)
+            side = ctypes.c_void_p(self.side.cuda_stream)
+            native.check(self.lib.svgt_peer_copy(ctypes.c_void_p(self._dst(half)), ctypes.c_void_p(self.outs[half].data_ptr()),
+                                                 self.counts[self.rank] * 80, side))
+            native.check(self.lib.svgt_set_flag(ctypes.c_void_p(self.flags + 4 * self.rank), self.step_no, side))
+            ev = self.torch.cuda.Event()
+            ev.record(self.side)
+            self.sent[half] = ev
+        elif self.mode == "nccl":
+            self.pending[half] = dist.gather(self.send[half], self.recv[half], dst=0, async_op=True)
+
+    def drain(self, stream):
+        """Everything sent so far has landed on rank 0 (enqueued on `stream`)."""
+        from svtyper_b200 import native
         if self.mode == "nccl":
             for h in (0, 1):
-                self.before_score(h)
+                self.before_score(stream, h)
+        elif self.mode == "dma":
+            for h in (0, 1):
+                if self.sent[h] is not None:
+                    stream.wait_event(self.sent[h])
+            if self.rank == 0 and self.step_no:
+                native.check(self.lib.svgt_wait_flags(ctypes.c_void_p(self.flags), self.world, self.step_no,
+                                                      ctypes.c_void_p(stream.cuda_stream)))
 
     def gathered_rows(self, half):
         """rank 0: all ranks' rows of the last step written into `half`, as OUT_DTYPE numpy rows."""
@@ -268,7 +310,7 @@ class RowGather(object):
         from svtyper_b200 import evidence as ev
         if self.rank != 0:
             return None
-        if self.mode == "peer":
+        if self.mode in ("peer", "dma"):
             from svtyper_b200 import native
             host = np.empty(self.total * 80, dtype=np.uint8)
             torch.cuda.synchronize()
@@ -279,7 +321,8 @@ class RowGather(object):
         return np.concatenate(parts, axis=0).reshape(-1).view(ev.OUT_DTYPE).copy()
 
     def close(self):
-        if self.mode == "peer":
+        if self.mode in ("peer", "dma"):
+            self.torch.cuda.synchronize()
             if self.rank == 0:
                 for p in self._owned:
                     self.lib.svgt_shared_free(ctypes.c_void_p(p))
@@ -296,15 +339,17 @@ def timed_steps(eng, dev, gather, steps, warmup, world, local_rank, stream):
 
     def step(i):
         half = i & 1
-        gather.before_score(half)
+        gather.before_score(stream, half)
         gather.arm(dev.desc, half)
         eng.score(dev, stream, out=gather.out_tensor(dev.out, half))
         gather.after_score(stream, half)
 
     for i in range(max(warmup, 3)):
         step(i)
-    gather.drain()
+    gather.drain(stream)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     eng.check(dev)
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,13 +362,13 @@ def timed_steps(eng, dev, gather, steps, warmup, world, local_rank, stream):
     ev0.record(stream)
     for i in range(steps):
         half = i & 1
-        gather.before_score(half)
+        gather.before_score(stream, half)
         gather.arm(dev.desc, half)
         k_ev[i][0].record(stream)
         eng.score(dev, stream, out=gather.out_tensor(dev.out, half))
         k_ev[i][1].record(stream)
         gather.after_score(stream, half)
-    gather.drain()
+    gather.drain(stream)
     ev1.record(stream)
     if world > 1:
         dist.barrier()
@@ -396,22 +441,31 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     dev = eng.upload(batch)
 
-    # ---- weak: every rank its own batch, all rows to rank 0
+    # ---- weak: every rank its own batch, all rows to rank 0 (once per requested gather route)
     counts = [batch.n_sites] * world
-    gather = RowGather(args.gather, rank, world, counts, device)
-    ms_total, kern_ms, clocks, launches, last_half = timed_steps(eng, dev, gather, args.steps, args.warmup, world, local_rank,
-                                                                 stream)
-    weak_value = world * batch.n_sites * args.steps / (ms_total * 1e-3)
+    modes = [m.strip() for m in args.gather.split(",") if m.strip()] or ["dma"]
     dev.desc.out_final = None                         # one plain pass: this rank's rows in its own buffer
     dev.desc.done_flag = None
     eng.score(dev, stream)
     own_rows = eng.rows(dev)
-    weak_gather_ok = None
-    if world > 1 and rank == 0:
-        g = gather.gathered_rows(last_half)
-        weak_gather_ok = bool(g[:batch.n_sites].tobytes() == own_rows.tobytes() and g.shape[0] == sum(counts))
-    gather_mode = gather.mode
-    gather.close()
+    weak_runs = []
+    for mi, mode in enumerate(modes if world > 1 else modes[:1]):
+        gather = RowGather(mode, rank, world, counts, device)
+        r_ms, r_kern, r_clocks, r_launches, r_half = timed_steps(eng, dev, gather, args.steps, args.warmup, world, local_rank,
+                                                                 stream)
+        ok = None
+        if world > 1 and rank == 0:
+            g = gather.gathered_rows(r_half)
+            ok = bool(g[:batch.n_sites].tobytes() == own_rows.tobytes() and g.shape[0] == sum(counts))
+        weak_runs.append({"gather": gather.mode, "requested": mode, "value": world * batch.n_sites * args.steps / (r_ms * 1e-3),
+                          "ms_per_step": r_ms / args.steps, "kernel_ms_avg_rank0": sum(r_kern) / len(r_kern),
+                          "gathered_rows_match": ok})
+        if mi == 0:
+            ms_total, kern_ms, clocks, launches, gather_mode, weak_gather_ok = r_ms, r_kern, r_clocks, r_launches, gather.mode, ok
+        gather.close()
+        dev.desc.out_final = None
+        dev.desc.done_flag = None
+    weak_value = world * batch.n_sites * args.steps / (ms_total * 1e-3)
 
     # ---- parity on the CPU sample (same sites, scored by the reference above)
     parity = None
@@ -443,7 +497,7 @@ def run_ours(args, rank, world, local_rank):
         rows_per_rank = [int(x) for x in t_rows.tolist()]
         sdev = eng.upload(my)
         scounts = [bounds[r + 1] - bounds[r] for r in range(world)]
-        sg = RowGather(args.gather, rank, world, scounts, device)
+        sg = RowGather(modes[0], rank, world, scounts, device)
         s_ms, s_kern, s_clocks, s_launches, s_half = timed_steps(eng, sdev, sg, args.steps, args.warmup, world, local_rank, stream)
         s_parity = None
         if rank == 0:
@@ -501,7 +555,7 @@ def run_ours(args, rank, world, local_rank):
         value = strong["value"] if primary_strong else weak_value
         ms_step = strong["ms_per_step"] if primary_strong else ms_total / args.steps
         weak = {"value": weak_value, "unit": UNIT, "ms_per_step": ms_total / args.steps, "sites_per_gpu": batch.n_sites,
-                "gather": gather_mode, "gathered_rows_match": weak_gather_ok}
+                "gather": gather_mode, "gathered_rows_match": weak_gather_ok, "routes": weak_runs}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -511,7 +565,8 @@ def run_ours(args, rank, world, local_rank):
                        "fragment_rows_per_gpu": batch.n_frag, "split_rows_per_gpu": batch.n_split,
                        "algorithmic_bytes_per_gpu": alg, "survey_8d_bytes_per_gpu": surv,
                        "l2": "inputs (%.2f GB) larger than L2" % (alg / 1e9),
-                       "gather": {"peer": "call kernels store their 80 B rows straight into rank 0's CUDA-IPC-mapped buffer over NVLink, one flag per rank; no collective in the step",
+                       "gather": {"dma": "each rank's copy engine forwards a finished step's 80 B rows into rank 0's CUDA-IPC-mapped buffer over NVLink under the next step's kernels, one flag per rank; no collective in the step",
+                                  "peer": "call kernels store their 80 B rows straight into rank 0's CUDA-IPC-mapped buffer over NVLink, one flag per rank; no collective in the step",
                                   "nccl": "nccl gather of 80 B rows to rank 0 every step, double-buffered under the next step",
                                   "none": "none"}[gather_mode],
                        "gen_seconds": round(t_gen, 1)},

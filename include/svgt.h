@@ -108,7 +108,7 @@ typedef struct svgt_cbatch {
     const double *logt;     int64_t n_log;
     const double *consts;                     /* [32]                                    */
     int32_t min_aligned, split_slop, assoc_mode;
-    int32_t unit_mode;                        /* 0 default; 1 / 2: fixed 8- / 2-site work units (tests) */
+    int32_t unit_mode;                        /* 0 default; 1 / 2: fixed full / 2-site work units (tests) */
     double split_weight, disc_weight;
     void *out_final;                          /* optional: the final 80-byte rows go HERE instead of out_rows
                                                  (e.g. a peer-mapped buffer of the gathering GPU); out_rows
@@ -168,13 +168,19 @@ int svgt_ctx_last_kernel_ms(const svgt_ctx_t *ctx, float *ms);
  * kernels write straight into over NVLink.  svgt_shared_alloc() cudaMalloc's `bytes` on the current
  * device and exports a 64-byte CUDA IPC handle; svgt_shared_open() maps such a handle in another
  * process (peer access is enabled by the mapping); svgt_wait_flags() enqueues, on `stream`, a wait until
- * flags[i] >= value for all i < n (flags: device memory of the current device).
+ * flags[i] >= value for all i < n (flags: device memory of the current device).  Two ways to fill such a buffer:
+ * the call kernel stores its rows there itself (svgt_cbatch_t::out_final / done_flag: the transfer sits at the end
+ * of the step), or svgt_peer_copy() + svgt_set_flag() forward a finished step's rows on a side stream -- the copy
+ * engines move them under the NEXT step's kernels (cudaMemcpyAsync over NVLink; the flag is set, with system
+ * scope, in stream order behind the copy).
  */
 int svgt_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[64]);
 int svgt_shared_open(const unsigned char handle[64], void **dev_ptr);
 int svgt_shared_close(void *dev_ptr);
 int svgt_shared_free(void *dev_ptr);
 int svgt_wait_flags(const int32_t *flags, int32_t n, int32_t value, void *stream);
+int svgt_peer_copy(void *dst, const void *src, int64_t bytes, void *stream);
+int svgt_set_flag(int32_t *flag, int32_t value, void *stream);
 int svgt_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes);   /* synchronous read-back of such a buffer */
 
 #ifdef __cplusplus

@@ -73,7 +73,30 @@ __global__ void svgt_wait_flags_kernel(const volatile int *flags, int n, int val
     __threadfence_system();
 }
 
+__global__ void svgt_set_flag_kernel(volatile int *flag, int value)
+{
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+
 extern "C" {
+
+int svgt_peer_copy(void *dst, const void *src, int64_t bytes, void *stream)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(SVGT_ERR_ARG, "bad %s", "svgt_peer_copy arguments");
+    if (bytes == 0) return SVGT_OK;
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "cudaMemcpyAsync(peer)");
+}
+
+int svgt_set_flag(int32_t *flag, int32_t value, void *stream)
+{
+    if (!flag) return fail(SVGT_ERR_ARG, "null %s", "flag");
+    svgt_set_flag_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SVGT_OK : cuda_fail(e, "svgt_set_flag launch");
+}
 
 int svgt_wait_flags(const int32_t *flags, int32_t n, int32_t value, void *stream)
 {

@@ -4,7 +4,7 @@
  * (reference singlesample.py:355-404: tally_variant_read_fragments; classic.py:286-435).
  *
  * Mapping (one persistent CTA per SM, work units claimed from an atomic cursor):
- *   - a warp owns a unit of up to G = 8 sites of the work-descending launch order and walks them in
+ *   - a warp owns a unit of up to G = 6 sites of the work-descending launch order and walks them in
  *     lock step: super-step k covers rows [32k, 32k + 32) of every site that still has rows -- first the
  *     fragment rows of the sites, then their split rows;
  *   - row delivery: at the start of super-step k lanes 0..G-1 each issue ONE cp.async.bulk (TMA 1-D,
@@ -27,11 +27,14 @@
 
 namespace {
 
-#ifndef SVGT_C_THREADS
-#define SVGT_C_THREADS 480          /* 15 warps x 13.6 KB of per-warp state + the per-CTA tables fill the 227 KB */
-#endif
 #ifndef SVGT_C_G
-#define SVGT_C_G 8
+#define SVGT_C_G 6                  /* sites per work unit.  Measured on the benchmark shape (1M sites): G = 6 with 20
+                                       warps 1.55 ms, G = 8 with 15 warps 1.59 ms, G = 4 with 28 / 24 / 20 warps
+                                       1.73 / 1.76 / 1.67 ms: fewer sites per unit buy resident warps (shared memory) but
+                                       thin out the 3 G chains of the ordered replay and the per-super-step overheads */
+#endif
+#ifndef SVGT_C_THREADS
+#define SVGT_C_THREADS 640          /* 20 warps x 10 KB of per-warp state + the per-CTA tables fill the 227 KB */
 #endif
 #ifndef SVGT_C_MINB
 #define SVGT_C_MINB 1
@@ -76,31 +79,33 @@ __host__ __device__ __forceinline__ long long c_hist_words(long long n_hist)
     return (n_hist < kCHistWordsMax ? n_hist : kCHistWordsMax) + kCHistPad;
 }
 
-/* unit ramp (see svgt_lean.cu: the heaviest sites are spread one per warp for small batches) */
+/* unit ramp: the launch order is work-descending, so for batches too small to amortise their longest unit the
+ * first W units (W = resident warps) hold one site each, the next W two, the next W four, the rest G: the
+ * heaviest sites are spread one per warp, the bulk keeps G-site interleaving for the ordered replay */
 struct CUnit { long long base; int count; };
 
 template <int G>
 __host__ __device__ __forceinline__ CUnit c_unit_range(long long unit, long long W, int ramp)
 {
     CUnit r;
-    if (!ramp || G < 8) { r.base = unit * G; r.count = G; return r; }
+    if (!ramp || G < 5) { r.base = unit * G; r.count = G; return r; }
     if (unit < W) { r.base = unit; r.count = 1; }
-    else if (ramp == 2) { r.base = W + (unit - W) * 8; r.count = 8; }
+    else if (ramp == 2) { r.base = W + (unit - W) * G; r.count = G; }
     else if (unit < 2 * W) { r.base = W + (unit - W) * 2; r.count = 2; }
     else if (unit < 3 * W) { r.base = 3 * W + (unit - 2 * W) * 4; r.count = 4; }
-    else { r.base = 7 * W + (unit - 3 * W) * 8; r.count = 8; }
+    else { r.base = 7 * W + (unit - 3 * W) * G; r.count = G; }
     return r;
 }
 
 template <int G>
 __host__ __device__ __forceinline__ long long c_n_units(long long n_sites, long long W, int ramp)
 {
-    if (!ramp || G < 8) return (n_sites + G - 1) / G;
+    if (!ramp || G < 5) return (n_sites + G - 1) / G;
     if (n_sites <= W) return n_sites;
-    if (ramp == 2) return W + (n_sites - W + 7) / 8;
+    if (ramp == 2) return W + (n_sites - W + G - 1) / G;
     if (n_sites <= 3 * W) return W + (n_sites - W + 1) / 2;
     if (n_sites <= 7 * W) return 2 * W + (n_sites - 3 * W + 3) / 4;
-    return 3 * W + (n_sites - 7 * W + 7) / 8;
+    return 3 * W + (n_sites - 7 * W + G - 1) / G;
 }
 
 __device__ __forceinline__ unsigned c_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -497,15 +502,16 @@ __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompac
     }
     /* multi-GPU: the last CTA to finish tells the gathering rank this shard's rows have landed */
     if (cp.done_flag) {
-        __shared__ int last;
-        __threadfence_system();
+        /* the CTA's rows are ordered before thread 0's system-scope fence by the barrier (fences are cumulative),
+         * so ONE fence per CTA publishes them; the last CTA's thread 0 has then observed every other CTA's count */
         __syncthreads();
-        if (threadIdx.x == 0) last = atomicAdd(p.status + 3, 1) == (int)gridDim.x - 1;
-        __syncthreads();
-        if (last && threadIdx.x == 0) {
+        if (threadIdx.x == 0) {
             __threadfence_system();
-            *reinterpret_cast<volatile int *>(cp.done_flag) = cp.done_value;
-            __threadfence_system();
+            if (atomicAdd(p.status + 3, 1) == (int)gridDim.x - 1) {
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(cp.done_flag) = cp.done_value;
+                __threadfence_system();
+            }
         }
     }
 }
@@ -563,7 +569,7 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream)
 
 int svgt_launch_compact(const SvgtCompactParams &cp, int unit_mode, cudaStream_t stream)
 {
-    /* unit_mode: 0 default (ramped units for small batches), 1 always G-site units, 2 two-site units */
+    /* unit_mode: 0 default (ramped units for small batches), 1 always G-site units, 2 always two-site units */
     if (unit_mode == 2) return launch_compact<2>(cp, 0, stream);
     return launch_compact<SVGT_C_G>(cp, unit_mode == 0 ? 1 : 0, stream);
 }

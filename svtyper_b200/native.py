@@ -25,7 +25,7 @@ SYMBOLS = ("svgt_abi_version", "svgt_last_error", "svgt_device_count", "svgt_sco
            "svgt_launches_per_batch", "svgt_set_variant", "svgt_ctx_create", "svgt_ctx_destroy",
            "svgt_ctx_score_host", "svgt_ctx_last_traffic", "svgt_ctx_last_kernel_ms",
            "svgt_score_compact", "svgt_ctx_score_host_compact", "svgt_shared_alloc", "svgt_shared_open",
-           "svgt_shared_close", "svgt_shared_free", "svgt_wait_flags", "svgt_memcpy_d2h")
+           "svgt_shared_close", "svgt_shared_free", "svgt_wait_flags", "svgt_memcpy_d2h", "svgt_peer_copy", "svgt_set_flag")
 LAYOUT_SITE_ORDER = 1
 
 
@@ -118,6 +118,10 @@ def lib():
         L.svgt_shared_close.argtypes = [ctypes.c_void_p]
         L.svgt_shared_free.restype = ctypes.c_int
         L.svgt_shared_free.argtypes = [ctypes.c_void_p]
+        L.svgt_peer_copy.restype = ctypes.c_int
+        L.svgt_peer_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.svgt_set_flag.restype = ctypes.c_int
+        L.svgt_set_flag.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
         L.svgt_memcpy_d2h.restype = ctypes.c_int
         L.svgt_memcpy_d2h.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.svgt_wait_flags.restype = ctypes.c_int

@@ -33,28 +33,37 @@ dev = eng.upload(local)
 eng.score(dev)
 rows = eng.rows(dev)
 full = shard.gather_rows(rows, bounds, rank, 2, device=torch.device("cuda", rank))
-exp = oracle.score(batch, n_threads=4)
+want = oracle.score(batch, n_threads=4)
+one = eng.upload(cb)                               # the whole batch on this rank's GPU: what the shards must add up to
+eng.score(one)
+exp = eng.rows(one)
+for k in ("GT", "GQ", "DP", "RO", "AO", "QR", "QA", "RS", "AS", "ASC", "RP", "AP", "GL"):
+    assert np.array_equal(exp[k], want[k]), k      # one GPU == oracle (SQ: device pow / log, compared to 1e-9 elsewhere)
 if rank == 0:
     got = shard.rows_from_tensor(full)
     assert got.tobytes() == exp.tobytes(), "nccl gather"
-# the collective-free path: rows stored by the call kernel into rank 0's buffer, one flag per rank
+# the collective-free routes: rows forwarded by the copy engine under the next step ("dma"), or stored by the call
+# kernel itself ("peer"), into rank 0's IPC-mapped buffer, one flag per rank
 counts = [bounds[1] - bounds[0], bounds[2] - bounds[1]]
-g = bench.RowGather("peer", rank, 2, counts, torch.device("cuda", rank))
 stream = torch.cuda.current_stream()
-for step in range(3):
-    g.before_score(step & 1)
-    g.arm(dev.desc, step & 1)
-    eng.score(dev, stream, out=g.out_tensor(dev.out, step & 1))
-    g.after_score(stream, step & 1)
-g.drain()
-torch.cuda.synchronize()
-dist.barrier()
-if rank == 0:
-    got = g.gathered_rows(0)
-    assert got.tobytes() == exp.tobytes(), "peer gather (%s)" % g.mode
-    print("gather mode", g.mode)
-dist.barrier()
-g.close()
+for mode in ("dma", "peer"):
+    g = bench.RowGather(mode, rank, 2, counts, torch.device("cuda", rank))
+    for step in range(3):
+        g.before_score(stream, step & 1)
+        g.arm(dev.desc, step & 1)
+        eng.score(dev, stream, out=g.out_tensor(dev.out, step & 1))
+        g.after_score(stream, step & 1)
+    g.drain(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        got = g.gathered_rows(0)
+        assert got.tobytes() == exp.tobytes(), "%s gather (%s)" % (mode, g.mode)
+        print("gather mode", mode, "->", g.mode)
+    dist.barrier()
+    g.close()
+    dev.desc.out_final = None
+    dev.desc.done_flag = None
 dist.destroy_process_group()
 '''
 
