@@ -16,10 +16,6 @@
  *   - phase A (score_cfrag_chunk / score_csplit_chunk): one row per lane, straight-line predicate chain;
  *     the three doubles a row yields {a + b, p_ref, p_alt} are parked structure-of-arrays -- p_ref / p_alt
  *     over the site's 512 bytes of the ring slot the rows were just read from, a + b beside it;
- *   - dense tails: the sites of a unit have similar lengths (the launch order is sorted by work), so their last,
- *     partial chunks fall into the same super-step; those rows are scored packed together -- lane i of dense
- *     chunk d takes row (32 d + i) of the concatenated tails, with its own site's constants -- instead of one
- *     mostly empty chunk per site (benchmark shape: 8.9 % fewer fragment chunks, 37 % fewer split chunks);
  *   - phase B after each super-step: lane 4g + c replays chain c of site g over the <= 32 parked rows in
  *     row order (the fp64 sums are order-sensitive: SURVEY.md H1), 3 G chains side by side;
  *   - the five sums of a site are parked in its 80-byte row of `out`; svgt_call_compact_kernel (one site
@@ -28,6 +24,8 @@
  *     another GPU: the multi-GPU gather without a collective).
  */
 #include "svgt_compact.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -43,8 +41,8 @@ namespace {
 #ifndef SVGT_C_MINB
 #define SVGT_C_MINB 1
 #endif
-#ifndef SVGT_C_DENSE
-#define SVGT_C_DENSE 1              /* the partial (< 32 row) chunks of a super-step are scored packed together */
+#ifndef SVGT_C_RAMP_PER_WARP_DEFAULT
+#define SVGT_C_RAMP_PER_WARP_DEFAULT 256
 #endif
 #ifndef SVGT_C_PREFETCH
 #define SVGT_C_PREFETCH 0
@@ -67,7 +65,6 @@ struct alignas(128) CWarpSmem {
     double spark[G][33];            /* parked a + b (or the two LUT indices where phase B needs a and b apart) */
     unsigned long long bar[kCD];    /* one mbarrier per slot */
     int cnt[2][8];                  /* [0] fragment rows, [1] split rows of each site (uniform reads) */
-    int dpre[8];                    /* dense tails: first dense index of each site's partial chunk in this super-step */
     SiteS site[G];
     CSiteF sf[G];
     CSplitF spf[G];
@@ -385,55 +382,6 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
                 if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
             };
-            /* ---- dense tails: which sites end in this super-step with a partial chunk, and is packing them worth it ---- */
-            unsigned dense_sites = 0u;                      /* bit g: site g's chunk of this super-step is scored in the dense pass */
-            int dense_tot = 0;
-#if SVGT_C_DENSE
-            {
-                int my_n = (lane < G ? cnts[lane < G ? lane : 0] : 0) - step * 32;
-                my_n = lane < G ? (my_n < 0 ? 0 : (my_n > 32 ? 32 : my_n)) : 0;
-                const int my_part = (my_n > 0 && my_n < 32) ? my_n : 0;
-                const unsigned pmask = __ballot_sync(full, my_part > 0);
-                const int tot = __reduce_add_sync(full, my_part);
-                const int nd = (tot + 31) >> 5;
-                if (nd < __popc(pmask)) {                   /* at least one chunk saved */
-                    int incl = my_part;
-#pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        const int up = __shfl_up_sync(full, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    if (lane < 8) ws.dpre[lane] = incl - my_part;
-                    __syncwarp();
-                    /* a row that continues the fragment of the row before it must sit right behind that row IN THE SAME
-                     * dense chunk: not so if it opens a site's partial chunk (the regular path's `lead` rows) or a dense
-                     * chunk; a WIDE split row needs its XEND row in the next lane.  Rare: such super-steps take the
-                     * regular path */
-                    bool bad = false;
-                    const unsigned contbit = sp ? CSP_FIRST : CF_CONT;
-                    auto flags_at = [&](const int idx) -> unsigned {        /* word 3 of the row at dense index idx */
-                        int g = 0;
-#pragma unroll
-                        for (int j = 1; j < G; ++j) g += idx >= ws.dpre[j];
-                        const int rj = idx - ws.dpre[g];
-                        unsigned w3;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(slotaddr + (unsigned)g * 528u + (unsigned)rj * 16u + 12u));
-                        return w3;
-                    };
-                    if (my_part > 0) {
-                        unsigned w3;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(slotaddr + (unsigned)lane * 528u + 12u));
-                        bad = sp ? !(w3 & contbit) : (w3 & contbit) != 0u;
-                    }
-                    if (lane > 0 && lane < nd) {
-                        const unsigned w3 = flags_at(32 * lane);
-                        bad = bad || (sp ? !(w3 & contbit) : (w3 & contbit) != 0u);
-                    }
-                    if (sp && lane < nd && 32 * lane + 31 < tot) bad = bad || (flags_at(32 * lane + 31) & CSP_WIDE) != 0u;
-                    if (!__any_sync(full, bad)) { dense_sites = pmask; dense_tot = tot; }
-                }
-            }
-#endif
             if (!sp) {
 #if SVGT_C_PREFETCH
                 /* the next site's row is fetched while this one is scored (parking only touches this site's bytes) */
@@ -451,11 +399,11 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                     int4 r = rn;
                     if (g + 1 < G) rn = raw_row(g + 1);
                     const int n = cnts[g] - step * 32;
-                    if (n <= 0 || ((dense_sites >> g) & 1u)) continue;
+                    if (n <= 0) continue;
                     if (lane >= n) r = make_int4(0, 0, 0, 0);
 #else
                     const int n = cnts[g] - step * 32;
-                    if (n <= 0 || ((dense_sites >> g) & 1u)) continue;
+                    if (n <= 0) continue;
                     const int4 r = load_row(g, n);
 #endif
                     __syncwarp();
@@ -469,7 +417,7 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
 #pragma unroll 1
                 for (int g = 0; g < G; ++g) {
                     const int n = cnts[g] - step * 32;
-                    if (n <= 0 || ((dense_sites >> g) & 1u)) continue;
+                    if (n <= 0) continue;
                     const int4 r = load_row(g, n);
                     __syncwarp();
                     const unsigned pk = slotaddr + (unsigned)g * 528u + (unsigned)lane * 8u;
@@ -479,56 +427,6 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                     if (so.lead) leads |= (unsigned long long)so.lead << (8 * g);
                 }
             }
-#if SVGT_C_DENSE
-            if (dense_sites) {
-                /* lane i of dense chunk d scores row 32 d + i of the concatenated partial chunks.  The next dense chunk's
-                 * rows are fetched before this one's results are parked: a site's tail spans at most two dense chunks,
-                 * and parking writes over its row bytes */
-                auto fetch = [&](const int d, int &g, int &rj, bool &valid) -> int4 {
-                    const int idx = 32 * d + lane;
-                    valid = idx < dense_tot;
-                    g = 0;
-#pragma unroll
-                    for (int j = 1; j < G; ++j) g += idx >= ws.dpre[j];
-                    rj = idx - ws.dpre[g];
-                    int4 r = make_int4(0, 0, 0, 0);
-                    if (valid)
-                        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                                     : "r"(slotaddr + (unsigned)g * 528u + (unsigned)rj * 16u));
-                    return r;
-                };
-                const int nd = (dense_tot + 31) >> 5;
-                int g0, rj0, g1 = 0, rj1 = 0;
-                bool v0, v1 = false;
-                int4 r0 = fetch(0, g0, rj0, v0), r1 = make_int4(0, 0, 0, 0);
-#pragma unroll 1
-                for (int d = 0; d < nd; ++d) {
-                    if (d + 1 < nd) r1 = fetch(d + 1, g1, rj1, v1);
-                    __syncwarp();
-                    const int nv = dense_tot - 32 * d;      /* rows in this dense chunk (>= 32: all lanes) */
-                    const unsigned pk = slotaddr + (unsigned)g0 * 528u + (unsigned)rj0 * 8u;
-                    if (!sp) {
-                        const CSiteF &F = ws.sf[g0];
-                        CRow a;
-                        crow_stage1(F, &ws.wf[g0][0], s_pm, r0, true, a);
-                        if (__any_sync(full, crow_is_rare(r0, a))) crow_stage2(p, t, ws.site[g0], F, s_lib, lane, nv, m, r0, a, err);
-                        const FragOut fo = crow_stage3<ASSOC>(lane, nv, r0, a);
-                        if (v0) {
-                            ws.spark[g0][rj0] = ASSOC == SVGT_ASSOC_CLASSIC ? __hiloint2double(fo.ib, fo.ia) : fo.s;
-                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(fo.p_ref) : "memory");
-                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
-                        }
-                    } else {
-                        const SplitOut so = score_csplit_chunk<ASSOC>(ws.spf[g0], s_pm, lane, nv, r0);
-                        if (v0) {
-                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(so.vseq) : "memory");
-                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(so.vclip) : "memory");
-                        }
-                    }
-                    r0 = r1; g0 = g1; rj0 = rj1; v0 = v1;
-                }
-            }
-#endif
             /* ---- phase B: the ordered replay of this super-step's parked rows ---- */
             __syncwarp();
             if (gb < G && c < (sp ? 2 : 3)) {
@@ -662,7 +560,13 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream)
     const long long want = (units + kCWarps - 1) / kCWarps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    if (ramp == 1 && p.n_sites >= 256 * cap * kCWarps) ramp = 0;       /* large batches amortise their longest unit */
+    /* large batches amortise their longest unit: no ramp above `ramp_sites` sites per resident warp
+     * (SVGT_C_RAMP_PER_WARP overrides the threshold for measurements) */
+    static const long long ramp_per_warp = [] {
+        const char *v = getenv("SVGT_C_RAMP_PER_WARP");
+        return v && *v ? atoll(v) : (long long)SVGT_C_RAMP_PER_WARP_DEFAULT;
+    }();
+    if (ramp == 1 && p.n_sites >= ramp_per_warp * cap * kCWarps) ramp = 0;
     SvgtCompactParams q = cp;
     q.ramp = ramp;
     kern<<<grid, SVGT_C_THREADS, smem, stream>>>(q);
