@@ -108,7 +108,10 @@ typedef struct svgt_cbatch {
     const double *logt;     int64_t n_log;
     const double *consts;                     /* [32]                                    */
     int32_t min_aligned, split_slop, assoc_mode;
-    int32_t unit_mode;                        /* 0 default; 1 / 2: fixed full / 2-site work units (tests) */
+    int32_t unit_mode;                        /* work units of the tally kernel: 0 ramped 1-2-4-6 sites when the batch is
+                                                 small (decided by site count); 1 always 6 sites; 3 always ramped --
+                                                 what a caller who has the sites' row counts should pick (ramp iff the
+                                                 six heaviest sites outweigh a warp's fair share); 2 two sites (tests) */
     double split_weight, disc_weight;
     void *out_final;                          /* optional: the final 80-byte rows go HERE instead of out_rows
                                                  (e.g. a peer-mapped buffer of the gathering GPU); out_rows

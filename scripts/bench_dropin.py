@@ -3,8 +3,8 @@
 (native evidence packer + CUDA engine) beside the reference's own `sso_genotype` (oracle/_ref, py3-patched,
 serial and with its own process pool) on the reference's fixture BAM and a VCF made of the fixture's 212
 records replicated K times (IDs made unique).  Output VCFs must be identical (modulo ##fileDate).
-Prints one JSON line.  Needs a GPU for this repo's arm; `--no-gpu` installs the oracle as scorer (CPU check
-of the plumbing only, not a product configuration)."""
+Prints one JSON line.  Needs a GPU for this repo's arm; `--no-gpu` patches the oracle over genotype.score (CPU check
+of the plumbing only, not a product configuration).  `--batch-size` / `--cores` are passed to this repo's arm."""
 import argparse
 import io
 import json
@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ref-cores", type=int, default=0, help="cores for the reference's pool (0 = all)")
     ap.add_argument("--no-gpu", action="store_true")
+    ap.add_argument("--batch-size", type=int, default=1000)
+    ap.add_argument("--cores", type=int, default=0)
     args = ap.parse_args()
     tmp = "/tmp/svgt_dropin_%d.vcf" % os.getpid()
     n_rec = replicated_vcf(args.reps, tmp)
@@ -52,12 +54,14 @@ def main():
     from svtyper_b200 import genotype, singlesample
     if args.no_gpu:
         from oracle import oracle
-        genotype.set_scorer(lambda batch, **p: oracle.score(batch, **p))
+        from svtyper_b200 import compact as cp
+        genotype.score = lambda batch, **p: oracle.score(cp.wide_from_compact(batch), **p)
 
     def ours():
         out = io.StringIO()
         with open(tmp) as fin:
-            singlesample.sso_genotype(BAM, fin, out, 20, 1, 1, 1000000, LIB, False, None, False, 1000, 1e10, None, 1000)
+            singlesample.sso_genotype(BAM, fin, out, 20, 1, 1, 1000000, LIB, False, None, False, 1000, 1e10,
+                                      args.cores or None, args.batch_size)
         return out.getvalue()
     ours()                                              # warm: CUDA context, library load
     t0 = time.perf_counter()
@@ -65,7 +69,9 @@ def main():
     t_ours = time.perf_counter() - t0
 
     from oracle import ref_loader
+    import resource
     res = {"metric": "sso_genotype wall time, whole function", "records": n_rec, "reps_of_fixture": args.reps,
+           "batch_size": args.batch_size, "max_rss_mb": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0,
            "ours": {"seconds": t_ours, "records_per_s": n_rec / t_ours,
                     "scorer": "oracle (CPU check)" if args.no_gpu else "CUDA engine"}}
     if ref_loader.ensure():

@@ -323,7 +323,7 @@ static int check_cbatch(const svgt_cbatch_t *b)
     if (!b->pm || !b->logt || !b->consts) return fail(SVGT_ERR_ARG, "null %s", "look-up tables");
     if (b->assoc_mode != SVGT_ASSOC_SSO && b->assoc_mode != SVGT_ASSOC_CLASSIC)
         return fail(SVGT_ERR_ARG, "bad %s", "assoc_mode");
-    if (b->unit_mode < 0 || b->unit_mode > 2) return fail(SVGT_ERR_ARG, "bad %s", "unit_mode");
+    if (b->unit_mode < 0 || b->unit_mode > 3) return fail(SVGT_ERR_ARG, "bad %s", "unit_mode");
     if (b->rows_min_aligned != b->min_aligned)
         return fail(SVGT_ERR_ARG, "%s: the rows were packed for another min_aligned", "rows_min_aligned");
     if (b->n_sites / 32 >= 0x7fffffffLL) return fail(SVGT_ERR_ARG, "too many %s", "sites");

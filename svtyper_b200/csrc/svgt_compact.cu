@@ -534,7 +534,7 @@ size_t c_smem_bytes(const SvgtParams &p)
 struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
 
 template <int G>
-int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream)
+int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, bool force_ramp = false)
 {
     static CLaunchInfo info[2] = {};
     const SvgtParams &p = cp.base;
@@ -566,7 +566,7 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream)
         const char *v = getenv("SVGT_C_RAMP_PER_WARP");
         return v && *v ? atoll(v) : (long long)SVGT_C_RAMP_PER_WARP_DEFAULT;
     }();
-    if (ramp == 1 && p.n_sites >= ramp_per_warp * cap * kCWarps) ramp = 0;
+    if (ramp == 1 && !force_ramp && p.n_sites >= ramp_per_warp * cap * kCWarps) ramp = 0;
     SvgtCompactParams q = cp;
     q.ramp = ramp;
     kern<<<grid, SVGT_C_THREADS, smem, stream>>>(q);
@@ -580,7 +580,9 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream)
 
 int svgt_launch_compact(const SvgtCompactParams &cp, int unit_mode, cudaStream_t stream)
 {
-    /* unit_mode: 0 default (ramped units for small batches), 1 always G-site units, 2 always two-site units */
+    /* unit_mode: 0 ramped units when the batch is small (by site count), 1 always G-site units, 2 always two-site
+     * units, 3 always ramped units (the caller knows the batch is heavy-tailed: Engine picks 1 or 3 from the sites'
+     * row counts) */
     if (unit_mode == 2) return launch_compact<2>(cp, 0, stream);
-    return launch_compact<SVGT_C_G>(cp, unit_mode == 0 ? 1 : 0, stream);
+    return launch_compact<SVGT_C_G>(cp, unit_mode == 1 ? 0 : 1, stream, unit_mode == 3);
 }

@@ -101,7 +101,7 @@ def _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_
     d.hist_max = int(batch.libs.hist.max()) if batch.libs.hist.size else 1
     d.pm, d.logt, d.n_log, d.consts = ptr["pm"], ptr["logt"], int(n_log), ptr["consts"]
     d.min_aligned, d.split_slop, d.assoc_mode = int(min_aligned), int(split_slop), int(assoc_mode)
-    d.unit_mode = int(unit_mode)
+    d.unit_mode = max(int(unit_mode), 0)
     d.split_weight, d.disc_weight = float(split_weight), float(disc_weight)
     d.flags = int(flags)
     d.rows_min_aligned = int(batch.min_aligned)
@@ -168,6 +168,8 @@ class Engine(object):
             out = np.zeros(batch.n_sites, dtype=ev.OUT_DTYPE)
         optr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
         if isinstance(batch, cp.CompactBatch):
+            if unit_mode == 0:
+                unit_mode = batch.suggest_unit_mode()
             desc = _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode,
                                 unit_mode, native.LAYOUT_SITE_ORDER if site_order else 0)
             rc = self._lib.svgt_ctx_score_host_compact(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
@@ -189,6 +191,8 @@ class Engine(object):
     # ---------------------------------------------------------------- device resident
     def upload(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
                assoc_mode=ev.ASSOC_SSO, unit_mode=0):
+        """unit_mode: 0 = pick from the batch's row counts (CompactBatch.suggest_unit_mode), else svgt_cbatch_t's
+        values (1 full units, 2 two-site units, 3 ramped units); -1 = leave the choice to the library (by site count)."""
         torch = _torch()
         arrs = host_arrays(batch, split_weight, disc_weight)
         tens = {}
@@ -199,6 +203,8 @@ class Engine(object):
             tens[k] = t.to(self.device)
         ptr = {k: t.data_ptr() for k, t in tens.items()}
         if isinstance(batch, cp.CompactBatch):
+            if unit_mode == 0:                      # auto: decided from the sites' row counts (we have them here)
+                unit_mode = batch.suggest_unit_mode()
             desc = _cdescriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
                                 disc_weight, assoc_mode, unit_mode, native.LAYOUT_SITE_ORDER)
         else:

@@ -117,6 +117,14 @@ def test_min_aligned_is_part_of_the_encoding(oracle):
         assert got.tobytes() == oracle.score(b, min_aligned=m).tobytes(), m
 
 
+def test_suggested_unit_mode_follows_the_tail():
+    heavy = cp.compact_from_wide(synth.generate("stress1m", n_sites=20000, seed=2))
+    even = cp.compact_from_wide(synth.generate("del1m4lib", n_sites=20000, seed=2))
+    assert heavy.suggest_unit_mode() == 3                      # a 5000-row site dwarfs a warp's share of 20k sites
+    assert even.suggest_unit_mode(resident_warps=8) == 1       # few warps: every warp has plenty of even units
+    assert cp.CompactBatch(even.sites, even.rows, even.libs).suggest_unit_mode() == 1     # no launch order
+
+
 def test_library_index_limit():
     b = synth.generate("del10k", n_sites=50, seed=1)
     bad = ev.EvidenceBatch(b.sites.copy(), b.frags.copy(), b.splits.copy(), b.libs)

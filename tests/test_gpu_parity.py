@@ -15,8 +15,9 @@ from util import assert_rows_match, INT_FIELDS
 
 pytestmark = pytest.mark.gpu
 
-# "c0" / "c1" / "c2": compact path with default / fixed 8-site / fixed 2-site work units; 0, 1: wide-row kernels
-PATHS = ["c0", "c1", "c2", 0, 1]
+# "c0" / "c1" / "c2" / "c3": compact path with work units chosen from the row counts / fixed full units / fixed
+# 2-site units / ramped units; "c9": choice left to the library (by site count); 0, 1: wide-row kernels
+PATHS = ["c0", "c1", "c2", "c3", "c9", 0, 1]
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +32,7 @@ def eng():
 def gpu_rows(eng, batch, path="c0", min_aligned=20, **kw):
     if isinstance(path, str):
         cb = batch if isinstance(batch, cp.CompactBatch) else cp.compact_from_wide(batch, min_aligned=min_aligned)
-        dev = eng.upload(cb, unit_mode=int(path[1]), min_aligned=min_aligned, **kw)
+        dev = eng.upload(cb, unit_mode=-1 if path == "c9" else int(path[1]), min_aligned=min_aligned, **kw)
     else:
         native.set_variant(path)
         dev = eng.upload(batch, min_aligned=min_aligned, **kw)
@@ -248,7 +249,7 @@ def test_idempotent_and_permutation_invariant(eng):
     permuting the site rows (with their offsets) permutes the output rows."""
     b = synth.generate("stress1m", n_sites=3000, seed=8)
     r1 = gpu_rows(eng, b, "c0")
-    for path in ("c0", "c1", "c2", 0, 1):
+    for path in PATHS:
         assert gpu_rows(eng, b, path).tobytes() == r1.tobytes(), path
     cb = cp.compact_from_wide(b)
     perm = np.random.default_rng(1).permutation(b.n_sites)
