@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="sites in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the site-sharded (strong) measurement")
+    ap.add_argument("--strong-only", action="store_true",
+                    help="N > 1: only rank 0 builds the global batch, the other ranks just their shard (for shapes whose "
+                         "per-rank copy would not fit the host: stress1m at 1M sites); implies --scaling strong")
     ap.add_argument("--gather", default="dma", help="comma-separated list of dma | peer | nccl; the first is the line's")
     return ap.parse_args()
 
@@ -384,6 +387,104 @@ def timed_steps(eng, dev, gather, steps, warmup, world, local_rank, stream):
     return ms_total, kern_ms, clocks, eng.launches - launches0, (steps - 1) & 1
 
 
+def measure_strong(args, rank, world, local_rank, device, eng, stream, batch, procs, modes, own_rows):
+    """ONE global batch (rank 0's), cut by shard.shard_bounds into contiguous site ranges balanced by evidence rows;
+    rank r regenerates and scores range r; all rows land on rank 0.  Returns the `strong` dict (rank 0's is complete)."""
+    import torch
+    import torch.distributed as dist
+    from svtyper_b200 import compact as cp, shard, synth
+    bounds = [0] * (world + 1)
+    if rank == 0:
+        bounds = shard.shard_bounds(batch, world)
+    dist.broadcast_object_list(bounds, src=0)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    if rank == 0:
+        my = batch.slice_sites(lo, hi)
+    else:
+        w = synth.generate_parallel(args.config, n_sites=args.sites, rank=0, procs=procs, site_range=(lo, hi), bucket=False)
+        my = cp.compact_from_wide(w)
+        del w
+    my.order = my.length_order()
+    t_rows = torch.zeros(world, dtype=torch.int64, device=device)
+    t_rows[rank] = my.n_rows
+    dist.all_reduce(t_rows)
+    rows_per_rank = [int(x) for x in t_rows.tolist()]
+    sdev = eng.upload(my)
+    scounts = [bounds[r + 1] - bounds[r] for r in range(world)]
+    sg = RowGather(modes[0], rank, world, scounts, device)
+    s_ms, s_kern, s_clocks, s_launches, s_half = timed_steps(eng, sdev, sg, args.steps, args.warmup, world, local_rank, stream)
+    s_parity = None
+    if rank == 0:
+        g = sg.gathered_rows(s_half)
+        s_parity = {"sites": int(g.shape[0]),
+                    "sharded_rows_byte_identical_to_one_gpu": bool(g.tobytes() == own_rows.tobytes())}
+    mean_rows = sum(rows_per_rank) / float(world)
+    strong = {"value": args.sites * args.steps / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / args.steps,
+              "sites_total": int(args.sites), "sites_per_rank": scounts, "rows_per_rank": rows_per_rank,
+              "row_imbalance": (max(rows_per_rank) / mean_rows - 1.0) if mean_rows else 0.0,
+              "kernel_ms_avg_rank0": sum(s_kern) / len(s_kern), "gather": sg.mode, "parity": s_parity,
+              "unit_mode": int(sdev.desc.unit_mode), "clocks": s_clocks, "gpu_launches": s_launches,
+              "partition": "shard.shard_bounds: contiguous site ranges balanced by evidence rows"}
+    sg.close()
+    del sdev
+    return strong
+
+
+def run_strong_only(args, rank, world, local_rank, device, eng, stream, batch, procs, t_gen):
+    """--strong-only: the global batch lives on rank 0 alone (host and GPU); prints a line whose value is the sharded run."""
+    import numpy as np
+    import torch.distributed as dist
+    from svtyper_b200 import evidence as ev
+    modes = [m.strip() for m in args.gather.split(",") if m.strip()] or ["dma"]
+    own_rows, one_ms, oracle_parity = None, None, None
+    if rank == 0:
+        import torch
+        dev = eng.upload(batch)
+        for _ in range(3):
+            eng.score(dev, stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            eng.score(dev, stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        one_ms = e0.elapsed_time(e1) / args.steps
+        own_rows = eng.rows(dev)
+        del dev
+        if not args.no_cpu_baseline:                  # the oracle (C restatement, all host threads) on a slice of the batch
+            from oracle import oracle
+            from svtyper_b200 import compact as cp
+            n = min(batch.n_sites, args.cpu_sample or 20000)
+            want = oracle.score(cp.wide_from_compact(batch.slice_sites(0, n)), n_threads=oracle.max_threads())
+            ok = all(np.array_equal(own_rows[:n][k], want[k]) for k in INT_FIELDS) and np.array_equal(own_rows[:n]["GL"], want["GL"])
+            gt = own_rows["GT"]
+            oracle_parity = {"sites": int(n), "int_fields_and_GL_bit_exact_vs_oracle": bool(ok),
+                             "skipped_rows": int((gt == ev.GT_SKIPPED).sum()), "blank_rows": int((gt == ev.GT_BLANK).sum()),
+                             "underflow_rows": int((gt == ev.GT_UNDERFLOW).sum())}
+    strong = measure_strong(args, rank, world, local_rank, device, eng, stream, batch, procs, modes, own_rows)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg, surv = batch.algorithmic_bytes(), batch.survey_bytes()
+        line = {
+            "metric": METRIC, "value": strong["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": strong["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sites_total": batch.n_sites, "schema": "compact (16 B rows, 48 B site rows)",
+                       "fragment_rows": batch.n_frag, "split_rows": batch.n_split, "algorithmic_bytes": alg,
+                       "survey_8d_bytes": surv, "gather": strong["gather"], "gen_seconds": round(t_gen, 1)},
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                         "one_gpu_ms_per_step": one_ms, "achieved": alg / (one_ms * 1e-3) / 1e9,
+                         "frac": alg / (one_ms * 1e-3) / 1e9 / peak, "frac_on_survey_8d_bytes": surv / (one_ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "note": "one GPU scoring the whole batch (rank 0), for reference"},
+            "one_gpu": {"value": batch.n_sites / (one_ms * 1e-3), "ms_per_step": one_ms},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": strong["gpu_launches"], "clocks": strong["clocks"],
+            "parity": oracle_parity, "strong": strong,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     from svtyper_b200 import compact as cp, evidence as ev, shard, synth
@@ -430,15 +531,24 @@ def run_ours(args, rank, world, local_rank):
         pinned[name] = t
         return t.numpy()
 
+    strong_only = bool(args.strong_only and world > 1)
+    if strong_only:
+        args.scaling = "strong"
     procs = max(2, min(32, cores // max(world, 1) - 1))
     t_gen = time.time()
-    wide = synth.generate_parallel(args.config, n_sites=args.sites, rank=rank, procs=procs)
-    batch = cp.compact_from_wide(wide, alloc=alloc)
-    del wide
+    if strong_only and rank != 0:
+        batch = None                                  # this rank only ever sees its shard of rank 0's batch (below)
+    else:
+        wide = synth.generate_parallel(args.config, n_sites=args.sites, rank=rank,
+                                       procs=max(2, min(32, cores - 2 * world)) if strong_only else procs)
+        batch = cp.compact_from_wide(wide, alloc=alloc)
+        del wide
     t_gen = time.time() - t_gen
 
     eng = engine.Engine(local_rank)
     stream = torch.cuda.current_stream()
+    if strong_only:
+        return run_strong_only(args, rank, world, local_rank, device, eng, stream, batch, procs, t_gen)
     dev = eng.upload(batch)
 
     # ---- weak: every rank its own batch, all rows to rank 0 (once per requested gather route)
@@ -478,40 +588,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- strong: rank 0's batch is THE global batch; rank r scores its row-balanced site range of it
     strong = None
     if world > 1 and not args.no_strong:
-        bounds = [0] * (world + 1)
-        if rank == 0:
-            bounds = shard.shard_bounds(batch, world)
-        dist.broadcast_object_list(bounds, src=0)
-        lo, hi = bounds[rank], bounds[rank + 1]
-        if rank == 0:
-            my = batch.slice_sites(lo, hi)
-        else:
-            w = synth.generate_parallel(args.config, n_sites=args.sites, rank=0, procs=procs, site_range=(lo, hi), bucket=False)
-            my = cp.compact_from_wide(w)
-            del w
-        my.order = my.length_order()
-        rows_per_rank = [0] * world
-        t_rows = torch.zeros(world, dtype=torch.int64, device=device)
-        t_rows[rank] = my.n_rows
-        dist.all_reduce(t_rows)
-        rows_per_rank = [int(x) for x in t_rows.tolist()]
-        sdev = eng.upload(my)
-        scounts = [bounds[r + 1] - bounds[r] for r in range(world)]
-        sg = RowGather(modes[0], rank, world, scounts, device)
-        s_ms, s_kern, s_clocks, s_launches, s_half = timed_steps(eng, sdev, sg, args.steps, args.warmup, world, local_rank, stream)
-        s_parity = None
-        if rank == 0:
-            g = sg.gathered_rows(s_half)
-            s_parity = {"sites": int(g.shape[0]),
-                        "sharded_rows_byte_identical_to_one_gpu": bool(g.tobytes() == own_rows.tobytes())}
-        mean_rows = sum(rows_per_rank) / float(world)
-        strong = {"value": args.sites * args.steps / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / args.steps,
-                  "sites_total": int(args.sites), "sites_per_rank": scounts, "rows_per_rank": rows_per_rank,
-                  "row_imbalance": (max(rows_per_rank) / mean_rows - 1.0) if mean_rows else 0.0,
-                  "kernel_ms_avg_rank0": sum(s_kern) / len(s_kern), "gather": sg.mode, "parity": s_parity,
-                  "partition": "shard.shard_bounds: contiguous site ranges balanced by evidence rows"}
-        sg.close()
-        del sdev
+        strong = measure_strong(args, rank, world, local_rank, device, eng, stream, batch, procs, modes, own_rows)
 
     # ---- end to end through the host-buffer C ABI call (pinned host -> H2D -> kernels -> D2H)
     arrs = engine.host_arrays(batch)

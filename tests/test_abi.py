@@ -109,3 +109,18 @@ def test_no_cpu_fallback(lib):
     from svtyper_b200 import engine
     with pytest.raises(native.SvgtError):
         engine.Engine()
+
+
+def test_torch_operator_is_registered():
+    """SURVEY 8b's inner seam as a torch op: registered with the documented schema; CPU tensors are refused
+    (there is no CPU implementation to dispatch to)."""
+    import torch
+    from svtyper_b200 import torch_op  # noqa: F401
+    op = torch.ops.svgt.score_batch
+    schema = str(op.default._schema)
+    assert "Tensor sites" in schema and "Tensor? order" in schema and "-> (Tensor, Tensor)" in schema
+    z = torch.zeros((1, 12), dtype=torch.int32)
+    with pytest.raises(Exception):
+        op(z, torch.zeros((0, 4), dtype=torch.int32), None, torch.zeros((1, 4), dtype=torch.float64),
+           torch.zeros((1, 4), dtype=torch.int32), torch.zeros(4, dtype=torch.int32), torch.zeros(256, dtype=torch.float64),
+           torch.zeros(8, dtype=torch.float64), torch.zeros(32, dtype=torch.float64), 1.0, 1.0, 20, 3, 0, 0)

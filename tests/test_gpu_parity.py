@@ -333,3 +333,19 @@ print("pipelined ok")
     env = dict(os.environ, SVGT_PIPELINE_MIN_SITES="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "pipelined ok" in r.stdout, r.stderr[-1500:]
+
+
+def test_torch_operator_matches_engine(eng, oracle):
+    """torch.ops.svgt.score_batch (device tensors in / out, current stream) gives the engine's bytes."""
+    import torch
+    from svtyper_b200 import engine, torch_op  # noqa: F401
+    b = synth.generate("mixed100k", n_sites=3000, seed=17)
+    cb = cp.compact_from_wide(b)
+    ref = gpu_rows(eng, cb, "c1")
+    arrs = engine.host_arrays(cb)
+    dev = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda() for k, v in arrs.items()}
+    out, status = torch.ops.svgt.score_batch(dev["sites"], dev["rows"], dev["order"], dev["lib_f64"], dev["lib_i32"], dev["hist"],
+                                             dev["pm"], dev["logt"], dev["consts"], 1.0, 1.0, 20, 3, ev.ASSOC_SSO, 1)
+    torch.cuda.synchronize()
+    assert int(status[0]) == 0
+    assert out.cpu().numpy().reshape(-1).view(ev.OUT_DTYPE).tobytes() == ref.tobytes()
