@@ -65,6 +65,7 @@ struct alignas(128) CWarpSmem {
     double spark[G][33];            /* parked a + b (or the two LUT indices where phase B needs a and b apart) */
     unsigned long long bar[kCD];    /* one mbarrier per slot */
     int cnt[2][8];                  /* [0] fragment rows, [1] split rows of each site (uniform reads) */
+    int lead[8];                    /* rows at the head of a site's chunk that continue the previous chunk's fragment */
     SiteS site[G];
     CSiteF sf[G];
     CSplitF spf[G];
@@ -73,7 +74,7 @@ struct alignas(128) CWarpSmem {
 };
 
 /* shared memory left for the cached histogram counts once the per-warp state and the per-CTA tables are placed */
-constexpr size_t kCFixedBytes = ((512 * sizeof(double) + SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF) + 127) & ~(size_t)127) +
+constexpr size_t kCFixedBytes = ((256 * sizeof(double) + SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF) + 127) & ~(size_t)127) +
                                 sizeof(CWarpSmem<SVGT_C_G>) * kCWarps;
 constexpr size_t kCSmemLimit = 227 * 1024;
 static_assert(kCFixedBytes + 4096 <= kCSmemLimit, "per-warp state does not fit the SM's shared memory");
@@ -177,8 +178,8 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
     const SvgtParams &p = cp.base;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_pm = reinterpret_cast<double *>(smem_raw);
-    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 512);     /* pm[0..255], then pm[q] / 2 (generic scorer) */
-    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
+    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 256);
+    size_t off = 256 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
     LibF *s_libf = reinterpret_cast<LibF *>(smem_raw + off);
     off += (kWLibs + 1) * sizeof(LibF);
     off = (off + 127) & ~(size_t)127;
@@ -190,14 +191,12 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
     const unsigned full = 0xffffffffu;
     int err = 0;
     const int nl = p.n_lib < SVGT_SMEM_LIBS ? p.n_lib : SVGT_SMEM_LIBS;
-    for (int i = tid; i < 256; i += SVGT_C_THREADS) {
-        const double v = p.pm[i];
-        s_pm[i] = v;
-        s_pm[256 + i] = __dmul_rn(v, 0.5);
-    }
+    for (int i = tid; i < 256; i += SVGT_C_THREADS) s_pm[i] = p.pm[i];
     for (int i = tid; i < nl; i += SVGT_C_THREADS) s_lib[i] = derive_lib(p, i, &err);
     WS &ws = s_warp[warp];
     if (lane < 2) ws.zero[lane] = 0.0;
+    if (lane < 8) ws.lead[lane] = 0;
+    const unsigned pm_addr = c_smem(s_pm);
     if (lane < kCD) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c_smem(&ws.bar[lane])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     /* the 32-bit form of 19 * h1 > h2 needs every histogram count below 2^26: the host states the largest
@@ -347,7 +346,6 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
 
         double sum_frag = 0.0, sum_split = 0.0;
         double acc = 0.0, pend = 0.0;
-        unsigned long long leads = 0ull;            /* `lead` of each site's chunk in this super-step, 8 bits per site */
 #pragma unroll 1
         for (int k = 0; k < kCD - 1 && k < T; ++k) issue(k, (tt + (unsigned)k) % (unsigned)kCD);
 #pragma unroll 1
@@ -370,17 +368,20 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                 int4 r;
                 asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                              : "r"(slotaddr + (unsigned)g * 528u + (unsigned)lane * 16u));
-                if (lane >= n) r = make_int4(0, 0, 0, 0);   /* the copy stopped at the site's last row */
+                /* the copy stopped at the site's last row: a row with zero flag / class words scores as nothing,
+                 * whatever the stale coordinates are */
+                if (lane >= n) { r.z = 0; r.w = 0; }
                 return r;
             };
-            auto park_frag = [&](const int g, const FragOut &fo) {
+            auto park_frag = [&](const int g, const int4 r, const CRow &a, const FragOut &fo) {
                 const unsigned pk = slotaddr + (unsigned)g * 528u + (unsigned)lane * 8u;
-                double s0 = fo.s;
-                if (ASSOC == SVGT_ASSOC_CLASSIC || (fo.lead > 0 && lane < fo.lead)) s0 = __hiloint2double(fo.ib, fo.ia);
-                ws.spark[g][lane] = s0;
+                ws.spark[g][lane] = ASSOC == SVGT_ASSOC_CLASSIC ? crow_lut_pair(r, a) : fo.s;
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(fo.p_ref) : "memory");
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
-                if (fo.lead) leads |= (unsigned long long)fo.lead << (8 * g);
+                if (ASSOC != SVGT_ASSOC_CLASSIC && __builtin_expect(fo.lead != 0, 0)) {       /* warp-uniform, rare */
+                    if (lane < fo.lead) ws.spark[g][lane] = crow_lut_pair(r, a);
+                    if (lane == 0) ws.lead[g] = fo.lead;
+                }
             };
             if (!sp) {
 #if SVGT_C_PREFETCH
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                     if (g + 1 < G) rn = raw_row(g + 1);
                     const int n = cnts[g] - step * 32;
                     if (n <= 0) continue;
-                    if (lane >= n) r = make_int4(0, 0, 0, 0);
+                    if (lane >= n) { r.z = 0; r.w = 0; }
 #else
                     const int n = cnts[g] - step * 32;
                     if (n <= 0) continue;
@@ -409,9 +410,9 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                     __syncwarp();
                     const CSiteF &F = ws.sf[g];
                     CRow a;
-                    crow_stage1(F, &ws.wf[g][0], s_pm, r, F.fast != 1, a);
+                    crow_stage1(F, &ws.wf[g][0], pm_addr, r, F.fast != 1, a);
                     if (__any_sync(full, crow_is_rare(r, a))) crow_stage2(p, t, ws.site[g], F, s_lib, lane, n, m, r, a, err);
-                    park_frag(g, crow_stage3<ASSOC>(lane, n, r, a));
+                    park_frag(g, r, a, crow_stage3<ASSOC>(lane, n, r, a));
                 }
             } else {
 #pragma unroll 1
@@ -421,10 +422,10 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                     const int4 r = load_row(g, n);
                     __syncwarp();
                     const unsigned pk = slotaddr + (unsigned)g * 528u + (unsigned)lane * 8u;
-                    const SplitOut so = score_csplit_chunk<ASSOC>(ws.spf[g], s_pm, lane, n, r);
+                    const SplitOut so = score_csplit_chunk<ASSOC>(ws.spf[g], pm_addr, lane, n, r);
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(so.vseq) : "memory");
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(so.vclip) : "memory");
-                    if (so.lead) leads |= (unsigned long long)so.lead << (8 * g);
+                    if (__builtin_expect(so.lead != 0, 0) && lane == 0) ws.lead[g] = so.lead;
                 }
             }
             /* ---- phase B: the ordered replay of this super-step's parked rows ---- */
@@ -432,14 +433,14 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
             if (gb < G && c < (sp ? 2 : 3)) {
                 int cnt = cnts[gb] - step * 32;
                 cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
-                const int lead = (int)(leads >> (8 * gb)) & 0xFF;
+                const int lead = ws.lead[gb];
                 const double *pr = reinterpret_cast<const double *>(&ws.ring[slot][gb][0]);
                 if (!sp) c_replay_frag<ASSOC>(c == 0 ? &ws.spark[gb][0] : pr + (c - 1) * 33, &ws.spark[gb][0], c, cnt, lead, s_pm,
                                               acc, pend);
                 else c_replay_split<ASSOC>(pr + c * 33, cnt, lead, acc, pend);
             }
-            leads = 0ull;
             __syncwarp();
+            if (lane < 8) ws.lead[lane] = 0;
             if (k == nsf - 1) {                             /* the fragment rows are done */
                 if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
                 sum_frag = acc; acc = 0.0; pend = 0.0;
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompac
 template <int G>
 size_t c_smem_bytes(const SvgtParams &p)
 {
-    size_t off = 512 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF);
+    size_t off = 256 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF);
     off = (off + 127) & ~(size_t)127;
     off += sizeof(CWarpSmem<G>) * kCWarps;
     off += (size_t)c_hist_words(p.n_hist) * sizeof(unsigned);

@@ -75,9 +75,7 @@ __device__ __noinline__ void slow_row(const SvgtParams &p, const Tables &t, cons
 /* one 32-row fragment chunk of site S scored by the warp (phase A): what every lane parks for its row */
 struct FragOut {
     double s, p_ref, p_alt;         /* ref_seq / ref_span / alt_span addends this row parks (see below)     */
-    int ia, ib;                     /* prob_mapq LUT indices of the row's own ref_seq addends a, b (0 = none) */
     int lead;                       /* warp-uniform: leading rows that continue the previous chunk's fragment */
-    bool need_idx;                  /* warp-uniform: phase B may read ia / ib of this chunk (lean kernel only)  */
 };
 
 /*
@@ -470,7 +468,14 @@ struct CRow { double hA, hB, wref, walt, pmA, pmB; int tie; unsigned vm, nm; boo
 
 /* stage 1: per-row loads (window constants of the row's library, prob_mapq of both reads) + the predicate chain;
  * `gen`: take the general chain (any site); otherwise the one-contig chain (F.fast == 1 sites only) */
-__device__ __forceinline__ void crow_stage1(const CSiteF &F, const WinF *wf, const double *s_pm, const int4 r, const bool gen,
+__device__ __forceinline__ double ld_pm(const unsigned pm_addr, const unsigned byte_off)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pm_addr + byte_off));
+    return v;
+}
+
+__device__ __forceinline__ void crow_stage1(const CSiteF &F, const WinF *wf, const unsigned pm_addr, const int4 r, const bool gen,
                                             CRow &st)
 {
     const int4 f0 = *reinterpret_cast<const int4 *>(&F.wA0);
@@ -479,9 +484,8 @@ __device__ __forceinline__ void crow_stage1(const CSiteF &F, const WinF *wf, con
     const unsigned lib = min((z >> 16) & kLibMaskC, (unsigned)kWLibs);
     const uint4 w0 = *reinterpret_cast<const uint4 *>(&wf[lib].altA_lo);
     const uint4 w1 = *reinterpret_cast<const uint4 *>(&wf[lib].FL);
-    const char *pmb = reinterpret_cast<const char *>(s_pm);
-    st.pmA = *reinterpret_cast<const double *>(pmb + ((z << 3) & 0x7F8u));
-    st.pmB = *reinterpret_cast<const double *>(pmb + ((z >> 5) & 0x7F8u));
+    st.pmA = ld_pm(pm_addr, (z << 3) & 0x7F8u);       /* prob_mapq of both reads: byte offsets (mapq * 8) out of the packed word */
+    st.pmB = ld_pm(pm_addr, (z >> 5) & 0x7F8u);
     if (!gen) crow_fast(r, f0, f1, w0, w1, st.hA, st.hB, st.wref, st.walt, st.tie);
     else crow_gen(r, f0, f1, *reinterpret_cast<const int4 *>(&F.sgnA), *reinterpret_cast<const uint4 *>(&F.mAA), w0, w1, st.hA,
                   st.hB, st.wref, st.walt, st.tie);
@@ -529,15 +533,14 @@ template <int ASSOC>
 __device__ __forceinline__ FragOut crow_stage3(const int lane, const int n, const int4 r, const CRow &st)
 {
     const unsigned full = 0xffffffffu;
-    const unsigned z = (unsigned)r.w;
     const double prod = __dmul_rn(st.pmA, st.pmB);
     const double vb = __dmul_rn(st.pmB, st.hB);
     FragOut o;
     o.s = __fma_rn(st.pmA, st.hA, vb);                 /* pmA * {0,1} is exact: one rounding, a + b */
     o.p_ref = __dmul_rn(prod, st.wref); o.p_alt = __dmul_rn(prod, st.walt);
-    o.ia = 0; o.ib = 0; o.lead = 0; o.need_idx = false;
+    o.lead = 0;
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
-        o.ia = st.hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = st.hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0;
+        /* phase B adds a and b one by one: the caller parks their LUT indices (crow_lut_pair) */
     } else if (st.special && ((st.vm & ~st.nm) & ~(st.nm << 1)) == 0u) {
         /* every continuation row sits right below the row that starts its fragment (and none leads the chunk):
          * one fold step -- the lower row takes (s_up + a) + b and the weights, the upper row parks zeros */
@@ -553,9 +556,17 @@ __device__ __forceinline__ FragOut crow_stage3(const int lane, const int n, cons
     } else if (st.special) {
         const FoldOut q = fold_continuations(lane, n, st.nm, st.vm, __dmul_rn(st.pmA, st.hA), vb, o.s, o.p_ref, o.p_alt);
         o.s = q.s; o.p_ref = q.p_ref; o.p_alt = q.p_alt; o.lead = q.lead;
-        if (lane < q.lead) { o.ia = st.hA != 0.0 ? (int)(z & 0xFFu) : 0; o.ib = st.hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0; }
     }
     return o;
+}
+
+/* the prob_mapq LUT indices of a row's own ref_seq addends a, b (0 = none), packed as a double: what phase B reads
+ * where it must add a and b apart (every row under the classic association, `lead` rows under the sso one) */
+__device__ __forceinline__ double crow_lut_pair(const int4 r, const CRow &st)
+{
+    const unsigned z = (unsigned)r.w;
+    const int ia = st.hA != 0.0 ? (int)(z & 0xFFu) : 0, ib = st.hB != 0.0 ? (int)((z >> 8) & 0xFFu) : 0;
+    return __hiloint2double(ib, ia);
 }
 
 /* ---- split rows (parsers.py:1122-1215, singlesample.py:262-274), pre-digested per site ---- */
@@ -582,7 +593,7 @@ __device__ __forceinline__ CSplitF make_csplitf(const SiteS &S, int slop)
 }
 
 template <int ASSOC>
-__device__ __forceinline__ SplitOut score_csplit_chunk(const CSplitF &F, const double *s_pm, const int lane, const int n,
+__device__ __forceinline__ SplitOut score_csplit_chunk(const CSplitF &F, const unsigned pm_addr, const int lane, const int n,
                                                        const int4 r)
 {
     const unsigned full = 0xffffffffu;
@@ -607,8 +618,8 @@ __device__ __forceinline__ SplitOut score_csplit_chunk(const CSplitF &F, const d
     const int kind = soft ? f0.w : 0;
     const bool Ls = kind == 0 ? lL : kind == 1 ? lR : kind == 2 ? (lL | lR) : false;
     const bool Rs = kind == 0 ? rRs : kind == 1 ? rLs : kind == 2 ? (rLs | rRs) : false;
-    const double x = s_pm[Ls ? (z & 0xFFu) : 0u];
-    const double y = s_pm[Rs ? ((z >> 8) & 0xFFu) : 0u];
+    const double x = ld_pm(pm_addr, Ls ? ((z << 3) & 0x7F8u) : 0u);
+    const double y = ld_pm(pm_addr, Rs ? ((z >> 5) & 0x7F8u) : 0u);
     const double p_alt = __dmul_rn(__dadd_rn(x, y), 0.5);       /* (.. + ..) / 2.0, exact either way */
     SplitOut o;
     o.vseq = soft ? 0.0 : p_alt; o.vclip = soft ? p_alt : 0.0; o.lead = 0;
