@@ -179,6 +179,14 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+def to_compact(wide, alloc):
+    """Wide synthetic rows -> the compact schema (native converter: threaded, no temporaries; numpy twin otherwise)."""
+    from svtyper_b200 import compact as cp, packer
+    if packer.available():
+        return packer.compact_from_wide(wide, min_aligned=20, alloc=alloc)
+    return cp.compact_from_wide(wide, alloc=alloc)
+
+
 class RowGather(object):
     """Where every rank's output rows end up: rank 0's buffer (see the module docstring for the three routes).
 
@@ -402,7 +410,7 @@ def measure_strong(args, rank, world, local_rank, device, eng, stream, batch, pr
         my = batch.slice_sites(lo, hi)
     else:
         w = synth.generate_parallel(args.config, n_sites=args.sites, rank=0, procs=procs, site_range=(lo, hi), bucket=False)
-        my = cp.compact_from_wide(w)
+        my = to_compact(w, None)
         del w
     my.order = my.length_order()
     t_rows = torch.zeros(world, dtype=torch.int64, device=device)
@@ -541,7 +549,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         wide = synth.generate_parallel(args.config, n_sites=args.sites, rank=rank,
                                        procs=max(2, min(32, cores - 2 * world)) if strong_only else procs)
-        batch = cp.compact_from_wide(wide, alloc=alloc)
+        batch = to_compact(wide, alloc)
         del wide
     t_gen = time.time() - t_gen
 

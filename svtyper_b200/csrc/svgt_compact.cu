@@ -378,10 +378,6 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                 ws.spark[g][lane] = ASSOC == SVGT_ASSOC_CLASSIC ? crow_lut_pair(r, a) : fo.s;
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk), "d"(fo.p_ref) : "memory");
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(pk + 264u), "d"(fo.p_alt) : "memory");
-                if (ASSOC != SVGT_ASSOC_CLASSIC && __builtin_expect(fo.lead != 0, 0)) {       /* warp-uniform, rare */
-                    if (lane < fo.lead) ws.spark[g][lane] = crow_lut_pair(r, a);
-                    if (lane == 0) ws.lead[g] = fo.lead;
-                }
             };
             if (!sp) {
 #if SVGT_C_PREFETCH
@@ -411,8 +407,17 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                     const CSiteF &F = ws.sf[g];
                     CRow a;
                     crow_stage1(F, &ws.wf[g][0], pm_addr, r, F.fast != 1, a);
-                    if (__any_sync(full, crow_is_rare(r, a))) crow_stage2(p, t, ws.site[g], F, s_lib, lane, n, m, r, a, err);
-                    park_frag(g, r, a, crow_stage3<ASSOC>(lane, n, r, a));
+                    if (__any_sync(full, crow_is_rare(r, a))) {     /* MULTI / CONT rows, ties: fix-ups, folds, lead rows */
+                        crow_stage2(p, t, ws.site[g], F, s_lib, lane, n, m, r, a, err);
+                        const FragOut fo = crow_stage3<ASSOC, true>(lane, n, r, a);
+                        park_frag(g, r, a, fo);
+                        if (ASSOC != SVGT_ASSOC_CLASSIC && fo.lead != 0) {                      /* warp-uniform */
+                            if (lane < fo.lead) ws.spark[g][lane] = crow_lut_pair(r, a);
+                            if (lane == 0) ws.lead[g] = fo.lead;
+                        }
+                    } else {
+                        park_frag(g, r, a, crow_stage3<ASSOC, false>(lane, n, r, a));
+                    }
                 }
             } else {
 #pragma unroll 1

@@ -529,7 +529,7 @@ __device__ __forceinline__ void crow_stage2(const SvgtParams &p, const Tables &t
 
 /* stage 3: the addends (singlesample.py:254-259: a = pm[A] if read A covers a breakend; :305-350: p_alt, p_ref),
  * continuation rows folded into their fragment's last row of the chunk (see the note above FragOut) */
-template <int ASSOC>
+template <int ASSOC, bool RARE>
 __device__ __forceinline__ FragOut crow_stage3(const int lane, const int n, const int4 r, const CRow &st)
 {
     const unsigned full = 0xffffffffu;
@@ -539,6 +539,7 @@ __device__ __forceinline__ FragOut crow_stage3(const int lane, const int n, cons
     o.s = __fma_rn(st.pmA, st.hA, vb);                 /* pmA * {0,1} is exact: one rounding, a + b */
     o.p_ref = __dmul_rn(prod, st.wref); o.p_alt = __dmul_rn(prod, st.walt);
     o.lead = 0;
+    if (!RARE) return o;                                /* no vote: the chunk has no continuation rows to fold */
     if (ASSOC == SVGT_ASSOC_CLASSIC) {
         /* phase B adds a and b one by one: the caller parks their LUT indices (crow_lut_pair) */
     } else if (st.special && ((st.vm & ~st.nm) & ~(st.nm << 1)) == 0u) {
