@@ -74,7 +74,7 @@ struct alignas(128) CWarpSmem {
 };
 
 /* shared memory left for the cached histogram counts once the per-warp state and the per-CTA tables are placed */
-constexpr size_t kCFixedBytes = ((256 * sizeof(double) + SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF) + 127) & ~(size_t)127) +
+constexpr size_t kCFixedBytes = 256 * sizeof(double) + ((SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF) + 127) & ~(size_t)127) +
                                 sizeof(CWarpSmem<SVGT_C_G>) * kCWarps;
 constexpr size_t kCSmemLimit = 227 * 1024;
 static_assert(kCFixedBytes + 4096 <= kCSmemLimit, "per-warp state does not fit the SM's shared memory");
@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
     typedef CWarpSmem<G> WS;
     const SvgtParams &p = cp.base;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s_pm = reinterpret_cast<double *>(smem_raw);
-    LibK *s_lib = reinterpret_cast<LibK *>(s_pm + 256);
-    size_t off = 256 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
+    __shared__ double s_pm[256];                            /* static: its shared address is a link-time constant */
+    LibK *s_lib = reinterpret_cast<LibK *>(smem_raw);
+    size_t off = (size_t)SVGT_SMEM_LIBS * sizeof(LibK);
     LibF *s_libf = reinterpret_cast<LibF *>(smem_raw + off);
     off += (kWLibs + 1) * sizeof(LibF);
     off = (off + 127) & ~(size_t)127;
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompac
 template <int G>
 size_t c_smem_bytes(const SvgtParams &p)
 {
-    size_t off = 256 * sizeof(double) + (size_t)SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF);
+    size_t off = (size_t)SVGT_SMEM_LIBS * sizeof(LibK) + (kWLibs + 1) * sizeof(LibF);
     off = (off + 127) & ~(size_t)127;
     off += sizeof(CWarpSmem<G>) * kCWarps;
     off += (size_t)c_hist_words(p.n_hist) * sizeof(unsigned);
