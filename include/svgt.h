@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SVGT_ABI_VERSION 2
+#define SVGT_ABI_VERSION 3
 
 #define SVGT_SITE_WORDS 16  /* int32 words per site row      (64 B) */
 #define SVGT_FRAG_WORDS 8   /* int32 words per fragment row  (32 B) */
@@ -87,6 +87,32 @@ typedef struct svgt_batch {
 } svgt_batch_t;
 
 /*
+ * Piece plan of a compact batch (optional; svgt_plan_count / svgt_plan_fill build it from the HOST site rows).
+ *
+ * The fp64 sums of a breakpoint run over its fragments in sorted(query_name) order (singlesample.py:364-378), so one
+ * warp walks a site's rows from first to last.  In a small or heavy-tailed batch (config `stress1m`: up to 10,000
+ * reads per site) the longest site then IS the run time.  With a plan, a site of more than `max_chunks` 32-row
+ * chunks is scored in pieces -- runs of whole chunks of its fragment rows or of its split rows, each handed to
+ * whichever warp is free -- whose per-row addends are parked in `scratch`; a second, small kernel then adds them
+ * up per site in row order.  Results are bit-identical with and without a plan.
+ *   entries  the launch list, heaviest first: a site index (>= 0; sites without rows are left out), or ~k for piece k
+ *   pieces   [n_pieces][4]  site, first row within the site's fragment (split) rows (a multiple of 32),
+ *            rows | (split rows ? 1 << 31 : 0), first scratch chunk
+ *   heavy    [n_heavy][4]   site, first scratch chunk, fragment chunks, split chunks -- one per site scored in pieces;
+ *            the site's chunks occupy scratch chunks [first, first + fragment chunks + split chunks) in row order
+ *   scratch  scratch_chunks * SVGT_PLAN_CHUNK_BYTES bytes of device memory, 16-byte aligned, contents don't matter
+ * Every pointer is a DEVICE pointer in svgt_score_compact(); svgt_ctx_score_host_compact() ignores `plan` and
+ * plans by itself.
+ */
+#define SVGT_PLAN_CHUNK_BYTES 784  /* 3 x 32 parked doubles + the chunk's lead-row count, padded to 16 bytes */
+typedef struct svgt_segplan {
+    const int32_t *entries; int64_t n_entries;
+    const int32_t *pieces;  int64_t n_pieces;
+    const int32_t *heavy;   int64_t n_heavy;
+    void *scratch;          int64_t scratch_chunks;
+} svgt_segplan_t;
+
+/*
  * The same batch in the COMPACT schema (svtyper_b200/compact.py; the default product path): 48-byte site
  * rows, and one array of 16-byte rows holding each site's fragment rows followed by its split rows.
  * In svgt_score_compact() every pointer is a DEVICE pointer; in svgt_ctx_score_host_compact() every
@@ -123,6 +149,8 @@ typedef struct svgt_cbatch {
     int32_t rows_min_aligned;                 /* the -m the packer evaluated the MULTI rows' is_ref_seq bits
                                                  with; must equal min_aligned (SVGT_ERR_ARG otherwise)     */
     int32_t reserved;
+    const svgt_segplan_t *plan;               /* optional piece plan (host struct, device pointers inside); with a
+                                                 plan `order` is not used: plan->entries is the launch list   */
 } svgt_cbatch_t;
 
 int svgt_abi_version(void);
@@ -139,6 +167,19 @@ int svgt_score_batch(const svgt_batch_t *batch, void *out_rows, int32_t *status,
 
 /* The same for a compact batch: the default path (svgt_compact_kernel + svgt_call_compact_kernel). */
 int svgt_score_compact(const svgt_cbatch_t *batch, void *out_rows, int32_t *status, void *stream);
+
+/*
+ * Build a piece plan from HOST site rows ([n_sites][12]).  svgt_plan_count() decides the piece length
+ * (*max_chunks; `force_chunks` > 0 dictates it, otherwise it grows with the batch so that no piece outlasts a small
+ * share of the batch's run time on `resident_warps` warps -- <= 0: those of the current device -- and is never
+ * below 4 chunks) and returns the array sizes; all four are 0 when no site is longer than a piece (score without a
+ * plan then).  svgt_plan_fill() writes the arrays (host memory of at least those sizes) for the same arguments.
+ */
+int svgt_plan_count(const int32_t *sites_host, int64_t n_sites, int32_t min_aligned, int32_t split_slop,
+                    int32_t resident_warps, int32_t force_chunks, int32_t *max_chunks, int64_t *n_entries,
+                    int64_t *n_pieces, int64_t *n_heavy, int64_t *scratch_chunks);
+int svgt_plan_fill(const int32_t *sites_host, int64_t n_sites, int32_t min_aligned, int32_t split_slop,
+                   int32_t max_chunks, int32_t *entries, int32_t *pieces, int32_t *heavy);
 
 /* Number of kernel launches svgt_score_batch issues for this batch (bench bookkeeping). */
 int svgt_launches_per_batch(const svgt_batch_t *batch);
@@ -163,6 +204,8 @@ int svgt_ctx_score_host(svgt_ctx_t *ctx, const svgt_batch_t *host_batch, void *o
 int svgt_ctx_score_host_compact(svgt_ctx_t *ctx, const svgt_cbatch_t *host_batch, void *out_rows_host);
 /* bytes moved by the last svgt_ctx_score_host call */
 int svgt_ctx_last_traffic(const svgt_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* pieces the last svgt_ctx_score_host_compact call cut its long sites into (0: it scored without a piece plan) */
+int svgt_ctx_last_pieces(const svgt_ctx_t *ctx, int64_t *n_pieces);
 /* device time (ms, CUDA events) of the kernel(s) in the last svgt_ctx_score_host call */
 int svgt_ctx_last_kernel_ms(const svgt_ctx_t *ctx, float *ms);
 

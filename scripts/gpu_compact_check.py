@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--no-wide", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--pieces", default="auto", help="piece plan of the timed compact batch: auto | off | <max chunks>")
     args = ap.parse_args()
     import torch
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
@@ -106,8 +107,15 @@ def main():
         time.time() - t0, cb.n_sites, cb.n_rows, cb.n_frag, cb.n_split, cb.algorithmic_bytes() / 1e9, cb.survey_bytes() / 1e9),
         flush=True)
     res = {"tag": args.tag, "lib": os.path.basename(native.LIB_PATH)}
-    for label, batch in ((("compact", cb),) + ((("wide-lean", wide),) if wide is not None else ())):
-        dev = eng.upload(batch)
+    plist = args.pieces.split(",")
+    runs = [("compact" if i == 0 else "compact_pieces_" + pc, cb, pc) for i, pc in enumerate(plist)]
+    if wide is not None:
+        runs.append(("wide-lean", wide, None))
+    for label, batch, pc in runs:
+        kw = {}
+        if pc is not None:
+            kw["piece_chunks"] = None if pc == "auto" else 0 if pc == "off" else int(pc)
+        dev = eng.upload(batch, **kw)
         for _ in range(3):
             eng.score(dev)
         torch.cuda.synchronize()
@@ -120,12 +128,16 @@ def main():
         eng.check(dev)
         ms = [a.elapsed_time(b_) for a, b_ in evs]
         res[label] = {"ms_avg": sum(ms) / len(ms), "ms_min": min(ms)}
+        if pc is not None:
+            res[label].update({"pieces": pc, "plan": dev.plan_info, "unit_mode": int(dev.desc.unit_mode),
+                               "frac_own_B": cb.algorithmic_bytes() / (res[label]["ms_avg"] * 1e-3) / 1e9 / 6545.9,
+                               "frac_survey_B": cb.survey_bytes() / (res[label]["ms_avg"] * 1e-3) / 1e9 / 6545.9})
         rows = eng.rows(dev)
         res[label]["gt_hist"] = np.bincount(rows["GT"] + 3, minlength=6).tolist()
         if label == "compact":
             keep = rows
         else:
-            res["identical_rows"] = bool(keep.tobytes() == rows.tobytes())
+            res[label]["identical_to_first"] = bool(keep.tobytes() == rows.tobytes())
         del dev
     k = res["compact"]["ms_avg"] * 1e-3
     res["compact"]["frac_own_B"] = cb.algorithmic_bytes() / k / 1e9 / 6545.9

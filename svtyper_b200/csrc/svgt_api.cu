@@ -176,13 +176,17 @@ struct svgt_ctx {
     cudaStream_t s_h2d, s_d2h;   /* pipelined path: copy streams either side of the kernels */
     cudaEvent_t ev0, ev1;
     cudaEvent_t up[kSlices], k0[kSlices], k1[kSlices];
-    void *buf[12];
-    size_t cap[12];
+    void *buf[16];
+    size_t cap[16];
+    int32_t *plan_host;          /* entries | pieces | heavy of the last planned batch (host staging) */
+    size_t plan_host_cap;
     int64_t h2d, d2h;
+    int64_t planned_pieces;      /* pieces of the last svgt_ctx_score_host_compact call (0: scored without a plan) */
     float kernel_ms;
 };
 
-enum { B_SITES, B_FRAGS, B_SPLITS, B_ORDER, B_LIBF, B_LIBI, B_HIST, B_PM, B_LOG, B_CONSTS, B_OUT, B_STATUS };
+enum { B_SITES, B_FRAGS, B_SPLITS, B_ORDER, B_LIBF, B_LIBI, B_HIST, B_PM, B_LOG, B_CONSTS, B_OUT, B_STATUS,
+       B_ENTRIES, B_PIECES, B_HEAVY, B_SCRATCH, B_COUNT };
 
 static int ctx_reserve(svgt_ctx *c, int slot, size_t bytes)
 {
@@ -238,8 +242,9 @@ int svgt_ctx_destroy(svgt_ctx_t *c)
 {
     if (!c) return SVGT_OK;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 12; ++i)
+    for (int i = 0; i < B_COUNT; ++i)
         if (c->buf[i]) cudaFree(c->buf[i]);
+    if (c->plan_host) cudaFreeHost(c->plan_host);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     for (int i = 0; i < kSlices; ++i) { cudaEventDestroy(c->up[i]); cudaEventDestroy(c->k0[i]); cudaEventDestroy(c->k1[i]); }
@@ -361,8 +366,148 @@ int svgt_score_compact(const svgt_cbatch_t *b, void *out_rows, int32_t *status, 
     cp.out_final = (svgt_out_row_t *)b->out_final;
     cp.done_flag = b->done_flag; cp.done_value = b->done_value;
     cp.hist_max = b->hist_max;
+    if (b->plan && b->plan->n_heavy > 0) {
+        const svgt_segplan_t *pl = b->plan;
+        if (pl->n_entries < 0 || pl->n_pieces < 0 || pl->scratch_chunks < 0 || !pl->entries || !pl->pieces || !pl->heavy ||
+            !pl->scratch || ((uintptr_t)pl->scratch & 15) || ((uintptr_t)pl->pieces & 15) || ((uintptr_t)pl->heavy & 15))
+            return fail(SVGT_ERR_ARG, "bad %s", "piece plan");
+        cp.entries = pl->entries; cp.n_entries = pl->n_entries;
+        cp.pieces = (const int4 *)pl->pieces; cp.n_pieces = pl->n_pieces;
+        cp.heavy = (const int4 *)pl->heavy; cp.n_heavy = pl->n_heavy;
+        cp.scratch = (double *)pl->scratch;
+        cp.scratch_lead = (int *)((char *)pl->scratch + (size_t)pl->scratch_chunks * 768);
+        cp.scratch_chunks = pl->scratch_chunks;
+    }
     e = (cudaError_t)svgt_launch_compact(cp, b->unit_mode, st);
     if (e != cudaSuccess) return cuda_fail(e, "svgt_compact_kernel launch");
+    return SVGT_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* piece plan (svgt_segplan_t)                                                           */
+/* ------------------------------------------------------------------------------------ */
+namespace {
+
+constexpr int kPlanMinChunks = 4;       /* shortest piece: below this the per-piece set-up outweighs the chunks */
+constexpr int kPlanShare = 14;          /* a piece may take 1/kPlanShare of a warp's fair share of the batch's chunks
+                                           (a lone piece advances ~3.5x slower than a warp among 20 busy ones: the
+                                           longest piece then costs about a quarter of the batch's run time) */
+constexpr int kPlanWarpsPerSm = 20;     /* SVGT_C_THREADS / 32 */
+
+/* rows of a site as the tally kernel will see them: SKIP sites and sites it refuses (svgt_device.cuh:
+ * site_fields_in_range, malformed counts) have none */
+inline void plan_site_chunks(const int32_t *row, int m, int slop, int &cf, int &cs)
+{
+    auto ok = [](int v, int lim) { return v > -lim && v < lim; };
+    const bool ranged = ok(row[0], 1 << 30) && ok(row[1], 1 << 30) && ok(row[2], 1 << 28) && ok(row[3], 1 << 28) &&
+                        ok(row[4], 1 << 28) && ok(row[5], 1 << 28) && m >= 0 && m < (1 << 20) && slop >= 0 && slop < (1 << 20);
+    const int nf = row[10], ns = row[11];
+    if ((row[7] & (1 << 4)) || !ranged || nf < 0 || ns < 0) { cf = 0; cs = 0; return; }
+    cf = (int)(((int64_t)nf + 31) >> 5); cs = (int)(((int64_t)ns + 31) >> 5);
+}
+
+int plan_resident_warps()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        sms = 148;
+    }
+    return sms * kPlanWarpsPerSm;
+}
+
+}  // namespace
+
+extern "C" int svgt_plan_count(const int32_t *sites, int64_t n_sites, int32_t min_aligned, int32_t split_slop,
+                               int32_t resident_warps, int32_t force_chunks, int32_t *max_chunks, int64_t *n_entries,
+                               int64_t *n_pieces, int64_t *n_heavy, int64_t *scratch_chunks)
+{
+    if (n_sites < 0 || (n_sites > 0 && !sites) || !max_chunks || !n_entries || !n_pieces || !n_heavy || !scratch_chunks)
+        return fail(SVGT_ERR_ARG, "bad %s", "svgt_plan_count arguments");
+    if (n_sites / 32 >= 0x7fffffffLL) return fail(SVGT_ERR_ARG, "too many %s", "sites");
+    *n_entries = *n_pieces = *n_heavy = *scratch_chunks = 0;
+    int64_t total = 0;
+    int longest = 0;
+    for (int64_t i = 0; i < n_sites; ++i) {
+        int cf, cs;
+        plan_site_chunks(sites + i * SVGT_CSITE_WORDS, min_aligned, split_slop, cf, cs);
+        total += (int64_t)cf + cs;
+        if (cf + cs > longest) longest = cf + cs;
+    }
+    int64_t L = force_chunks;
+    if (L <= 0) {
+        const int64_t warps = resident_warps > 0 ? resident_warps : plan_resident_warps();
+        static const long long min_chunks = [] {
+            const char *v = getenv("SVGT_PLAN_MIN_CHUNKS");
+            return v && *v && atoll(v) > 0 ? atoll(v) : (long long)kPlanMinChunks;
+        }();
+        L = (total + kPlanShare * warps - 1) / (kPlanShare * warps);
+        if (L < min_chunks) L = min_chunks;
+    }
+    if (L > 0x3ffffff) L = 0x3ffffff;
+    *max_chunks = (int32_t)L;
+    if (longest <= L) return SVGT_OK;                       /* nothing to cut */
+    int64_t ne = 0, np = 0, nh = 0, sc = 0;
+    for (int64_t i = 0; i < n_sites; ++i) {
+        int cf, cs;
+        plan_site_chunks(sites + i * SVGT_CSITE_WORDS, min_aligned, split_slop, cf, cs);
+        if (cf + cs == 0) continue;
+        if (cf + cs <= L) { ++ne; continue; }
+        const int64_t k = (cf + L - 1) / L + (cs + L - 1) / L;
+        ++nh; np += k; ne += k; sc += (int64_t)cf + cs;
+    }
+    if (np >= 0x7fffffffLL || sc >= 0x7fffffffLL || ne >= 0x7fffffffLL) return fail(SVGT_ERR_ARG, "too many %s", "pieces");
+    *n_entries = ne; *n_pieces = np; *n_heavy = nh; *scratch_chunks = sc;
+    return SVGT_OK;
+}
+
+extern "C" int svgt_plan_fill(const int32_t *sites, int64_t n_sites, int32_t min_aligned, int32_t split_slop,
+                              int32_t max_chunks, int32_t *entries, int32_t *pieces, int32_t *heavy)
+{
+    if (n_sites < 0 || (n_sites > 0 && !sites) || max_chunks <= 0 || !entries || !pieces || !heavy)
+        return fail(SVGT_ERR_ARG, "bad %s", "svgt_plan_fill arguments");
+    const int64_t L = max_chunks;
+    /* counting sort of the entries by chunk count, heaviest first (an entry has 1..L chunks) */
+    int64_t *start = (int64_t *)calloc((size_t)L + 2, sizeof(int64_t));
+    if (!start) return fail(SVGT_ERR_ARG, "out of %s", "host memory");
+    for (int64_t i = 0; i < n_sites; ++i) {
+        int cf, cs;
+        plan_site_chunks(sites + i * SVGT_CSITE_WORDS, min_aligned, split_slop, cf, cs);
+        if (cf + cs == 0) continue;
+        if (cf + cs <= L) { ++start[cf + cs]; continue; }
+        for (int part = 0; part < 2; ++part)
+            for (int64_t c0 = 0, n = part ? cs : cf; c0 < n; c0 += L) ++start[n - c0 < L ? n - c0 : L];
+    }
+    {
+        int64_t at = 0;
+        for (int64_t w = L; w >= 1; --w) { const int64_t n = start[w]; start[w] = at; at += n; }
+    }
+    int64_t np = 0, nh = 0, sc = 0;
+    for (int64_t i = 0; i < n_sites; ++i) {
+        const int32_t *row = sites + i * SVGT_CSITE_WORDS;
+        int cf, cs;
+        plan_site_chunks(row, min_aligned, split_slop, cf, cs);
+        if (cf + cs == 0) continue;
+        if (cf + cs <= L) { entries[start[cf + cs]++] = (int32_t)i; continue; }
+        int32_t *h = heavy + nh * 4;
+        h[0] = (int32_t)i; h[1] = (int32_t)sc; h[2] = cf; h[3] = cs;
+        ++nh;
+        for (int part = 0; part < 2; ++part) {
+            const int64_t n = part ? cs : cf, rows = part ? row[11] : row[10];
+            for (int64_t c0 = 0; c0 < n; c0 += L) {
+                const int64_t w = n - c0 < L ? n - c0 : L;
+                const int64_t r0 = c0 * 32, cnt = rows - r0 < w * 32 ? rows - r0 : w * 32;
+                int32_t *q = pieces + np * 4;
+                q[0] = (int32_t)i; q[1] = (int32_t)r0;
+                q[2] = (int32_t)((uint32_t)cnt | (part ? 0x80000000u : 0u));
+                q[3] = (int32_t)(sc + (part ? cf : 0) + c0);
+                entries[start[w]++] = (int32_t)~np;
+                ++np;
+            }
+        }
+        sc += (int64_t)cf + cs;
+    }
+    free(start);
     return SVGT_OK;
 }
 
@@ -420,6 +565,8 @@ static int ctx_score_pipelined_compact(svgt_ctx *c, const svgt_cbatch_t *hb, voi
     if ((rc = ctx_reserve(c, B_OUT, (size_t)n * SVGT_OUT_BYTES)) != SVGT_OK) goto fail_out;
     if ((rc = ctx_reserve(c, B_STATUS, 16 * kSlices)) != SVGT_OK) goto fail_out;
     db.order = nullptr;                               /* the launch permutation spans the whole batch */
+    db.plan = nullptr;                                /* slices of >= 16k sites each: throughput-bound, no pieces */
+    c->planned_pieces = 0;
     db.rows = (const int32_t *)c->buf[B_FRAGS];
     for (int k = 0; k < kSlices; ++k) {
         const int64_t s0 = cut_s[k], s1 = cut_s[k + 1];
@@ -522,6 +669,53 @@ int svgt_ctx_score_host_compact(svgt_ctx_t *c, const svgt_cbatch_t *hb, void *ou
     if ((rc = ctx_reserve(c, B_OUT, (size_t)hb->n_sites * SVGT_OUT_BYTES)) != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
     if ((rc = ctx_reserve(c, B_STATUS, 16)) != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
 
+    /* the host has the site rows: cut sites that are too long for one warp into pieces (svgt_segplan_t);
+     * SVGT_PLAN=0 disables, SVGT_PLAN_FORCE_CHUNKS dictates the piece length (tests) */
+    svgt_segplan_t plan;
+    memset(&plan, 0, sizeof(plan));
+    db.plan = nullptr;
+    static const long long plan_mode = [] {
+        const char *v = getenv("SVGT_PLAN");
+        return v && *v ? atoll(v) : 1LL;
+    }();
+    if (plan_mode != 0 && hb->n_sites > 0 && hb->unit_mode != 2) {
+        const char *fv = getenv("SVGT_PLAN_FORCE_CHUNKS");
+        const int32_t force = fv && *fv ? (int32_t)atoi(fv) : 0;
+        int32_t L = 0;
+        int64_t ne = 0, np = 0, nh = 0, sc = 0;
+        rc = svgt_plan_count(hb->sites, hb->n_sites, hb->min_aligned, hb->split_slop, 0, force, &L, &ne, &np, &nh, &sc);
+        if (rc != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
+        if (nh > 0) {
+            const size_t words = (size_t)ne + (size_t)np * 4 + (size_t)nh * 4 + 8;
+            if (c->plan_host_cap < words) {
+                /* earlier plans may still be in flight from this staging buffer only within a call that has returned */
+                if (c->plan_host) cudaFreeHost(c->plan_host);
+                c->plan_host = nullptr; c->plan_host_cap = 0;
+                if ((e = cudaMallocHost((void **)&c->plan_host, (words + words / 4) * sizeof(int32_t))) != cudaSuccess) {
+                    cudaStreamSynchronize(c->stream);
+                    return cuda_fail(e, "cudaMallocHost(plan)");
+                }
+                c->plan_host_cap = words + words / 4;
+            }
+            int32_t *h_entries = c->plan_host;
+            int32_t *h_pieces = h_entries + (((size_t)ne + 3) & ~(size_t)3);
+            int32_t *h_heavy = h_pieces + (size_t)np * 4;
+            rc = svgt_plan_fill(hb->sites, hb->n_sites, hb->min_aligned, hb->split_slop, L, h_entries, h_pieces, h_heavy);
+            if (rc == SVGT_OK) rc = ctx_upload(c, B_ENTRIES, h_entries, (size_t)ne * 4);
+            if (rc == SVGT_OK) rc = ctx_upload(c, B_PIECES, h_pieces, (size_t)np * 16);
+            if (rc == SVGT_OK) rc = ctx_upload(c, B_HEAVY, h_heavy, (size_t)nh * 16);
+            if (rc == SVGT_OK) rc = ctx_reserve(c, B_SCRATCH, (size_t)sc * SVGT_PLAN_CHUNK_BYTES);
+            if (rc != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
+            plan.entries = (const int32_t *)c->buf[B_ENTRIES]; plan.n_entries = ne;
+            plan.pieces = (const int32_t *)c->buf[B_PIECES]; plan.n_pieces = np;
+            plan.heavy = (const int32_t *)c->buf[B_HEAVY]; plan.n_heavy = nh;
+            plan.scratch = c->buf[B_SCRATCH]; plan.scratch_chunks = sc;
+            db.plan = &plan;
+            db.unit_mode = 3;                               /* heaviest entries first, one per warp */
+        }
+    }
+    c->planned_pieces = db.plan ? plan.n_pieces : 0;
+
     cudaEventRecord(c->ev0, c->stream);
     rc = svgt_score_compact(&db, c->buf[B_OUT], (int32_t *)c->buf[B_STATUS], c->stream);
     if (rc != SVGT_OK) { cudaStreamSynchronize(c->stream); return rc; }
@@ -605,6 +799,13 @@ int svgt_ctx_last_traffic(const svgt_ctx_t *c, int64_t *h2d_bytes, int64_t *d2h_
     if (!c) return fail(SVGT_ERR_ARG, "null %s", "ctx");
     if (h2d_bytes) *h2d_bytes = c->h2d;
     if (d2h_bytes) *d2h_bytes = c->d2h;
+    return SVGT_OK;
+}
+
+int svgt_ctx_last_pieces(const svgt_ctx_t *c, int64_t *n_pieces)
+{
+    if (!c || !n_pieces) return fail(SVGT_ERR_ARG, "null %s", "ctx/n_pieces");
+    *n_pieces = c->planned_pieces;
     return SVGT_OK;
 }
 

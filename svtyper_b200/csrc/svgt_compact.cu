@@ -171,7 +171,15 @@ __device__ __forceinline__ void c_replay_split(const double *px, int cnt, int le
     }
 }
 
-template <int G, int ASSOC>
+/*
+ * SEG: the launch list (cp.entries) names sites AND pieces of sites.  A piece is a run of whole 32-row chunks of
+ * one site's fragment rows or split rows; the warp scores it like a site of its own (phase A is per chunk, so the
+ * addends are the ones the unsplit site would park), but instead of summing them it copies each chunk's parked
+ * addends to cp.scratch -- the order-sensitive sums of such a site are made afterwards, in row order, by
+ * svgt_replay_pieces_kernel.  That takes a long site off the critical path of a small or heavy-tailed batch: its
+ * chunks are scored by many warps at once, and the serial part left is one DADD per row.
+ */
+template <int G, int ASSOC, bool SEG>
 __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kernel(const SvgtCompactParams cp)
 {
     typedef CWarpSmem<G> WS;
@@ -245,7 +253,8 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
     const int gb = lane >> 2, c = lane & 3;                 /* phase-B role: chain c of site gb */
     const int ramp = cp.ramp;
     const long long W = (long long)gridDim.x * kCWarps;
-    const long long n_units = c_n_units<G>(p.n_sites, W, ramp);
+    const long long n_entries = SEG ? cp.n_entries : p.n_sites;
+    const long long n_units = c_n_units<G>(n_entries, W, ramp);
     unsigned tt = 0u;                                       /* super-steps consumed by this warp (slot / phase) */
 
     long long unit = 0, unit_next = 0;
@@ -255,15 +264,25 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
         /* ---- lanes 0..G-1 read their site row and publish the scalars ---- */
         int my_nf = 0, my_ns = 0;
         const int4 *my_rows = cp.rows;
+        unsigned segmask = 0u;                              /* SEG: sites of this unit that are pieces */
         {
             const CUnit ur = c_unit_range<G>(unit, W, ramp);
             const long long idx = ur.base + lane;
-            const bool valid = lane < ur.count && lane < G && idx < p.n_sites;
+            const bool valid = lane < ur.count && lane < G && idx < n_entries;
             long long site = 0;
             bool valid2 = valid;
+            int4 pc = make_int4(0, 0, 0, 0);                /* SEG: the piece (site, first row, rows | split << 31, scratch chunk) */
+            bool is_piece = false;
             if (valid) {
-                site = p.order ? (long long)p.order[idx] : idx;
-                if (site < 0 || site >= p.n_sites) { site = 0; valid2 = false; err = SVGT_ERR_ARG; }   /* bad order[] entry */
+                if (SEG) {
+                    const int e = cp.entries[idx];
+                    if (e < 0) {
+                        const long long k = (long long)~e;
+                        if (k < cp.n_pieces) { pc = ldg4(cp.pieces + k); site = pc.x; is_piece = true; }
+                        else site = -1;
+                    } else site = e;
+                } else site = p.order ? (long long)p.order[idx] : idx;
+                if (site < 0 || site >= p.n_sites) { site = 0; valid2 = false; is_piece = false; err = SVGT_ERR_ARG; }   /* bad entry */
             }
             int4 a = make_int4(0, 0, 0, 0), b = a, d = a;
             if (valid2) {
@@ -278,7 +297,22 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
             const long long roff = ((long long)(unsigned)d.x) | ((long long)d.y << 32);
             int nf = run ? d.z : 0, ns = run ? d.w : 0;
             if (nf < 0 || ns < 0 || roff < 0 || roff + nf + ns > cp.n_rows) { nf = 0; ns = 0; err = SVGT_ERR_ARG; }
-            my_nf = nf; my_ns = ns; my_rows = cp.rows + roff;
+            long long prow = roff;
+            if (SEG && is_piece) {
+                /* whole chunks of one part of the site: chunk boundaries are the unsplit site's */
+                const int cnt = pc.z & 0x7fffffff;
+                const bool psplit = pc.z < 0;
+                const int part = psplit ? ns : nf;
+                if (pc.y < 0 || (pc.y & 31) || cnt <= 0 || cnt > part - pc.y || pc.w < 0 ||
+                    (long long)pc.w + ((cnt + 31) >> 5) > cp.scratch_chunks) {
+                    nf = 0; ns = 0; is_piece = false; err = SVGT_ERR_ARG;
+                } else {
+                    prow = roff + (psplit ? nf : 0) + pc.y;
+                    nf = psplit ? 0 : cnt; ns = psplit ? cnt : 0;
+                }
+            }
+            if (SEG) segmask = __ballot_sync(full, is_piece) & ((1u << G) - 1u);
+            my_nf = nf; my_ns = ns; my_rows = cp.rows + prow;
             if (lane < G) {
                 SiteS &S = ws.site[lane];
                 const int same = (meta >> 5) & 1;
@@ -287,9 +321,9 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
                 S.meta = (meta & 15) | ((a.x - m >= 0) << 8) | ((a.y - m >= 0) << 9);
                 S.var_length = b.z;
                 S.posA = a.x; S.posB = a.y; S.ciA0 = a.z; S.ciA1 = a.w; S.ciB0 = b.x; S.ciB1 = b.y;
-                S.dAB = a.y - a.x; S.nf = nf; S.foff = roff; S.soff = roff + nf; S.ns = ns;
-                S.slot = valid2 ? (int)site : -1;
-                S.pad1 = 0; S.pad2 = 0;
+                S.dAB = a.y - a.x; S.nf = nf; S.foff = prow; S.soff = prow + nf; S.ns = ns;
+                S.slot = (valid2 && !(SEG && is_piece)) ? (int)site : -1;   /* a piece's sums are made by the replay kernel */
+                S.pad1 = pc.w; S.pad2 = 0;                                  /* pad1: the piece's first scratch chunk */
                 CSiteF &F = ws.sf[lane];
                 const int svtype = meta & 3;
                 F.wA0 = a.x - m; F.wA1 = a.x + m; F.wB0 = a.y - m; F.wB1 = a.y + m;
@@ -435,7 +469,20 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
             }
             /* ---- phase B: the ordered replay of this super-step's parked rows ---- */
             __syncwarp();
-            if (gb < G && c < (sp ? 2 : 3)) {
+            if (SEG && segmask) {                           /* pieces: the chunk's parked addends (and its lead count) go to scratch */
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    if (!((segmask >> g) & 1u) || cnts[g] - step * 32 <= 0) continue;
+                    const long long q = (long long)ws.site[g].pad1 + step;
+                    double *dst = cp.scratch + q * 96;
+                    const double *pr = reinterpret_cast<const double *>(&ws.ring[slot][g][0]);
+                    dst[lane] = ws.spark[g][lane];
+                    dst[32 + lane] = pr[lane];
+                    dst[64 + lane] = pr[33 + lane];
+                    if (lane == 0) cp.scratch_lead[q] = ws.lead[g];
+                }
+            }
+            if (gb < G && c < (sp ? 2 : 3) && !(SEG && ((segmask >> gb) & 1u))) {
                 int cnt = cnts[gb] - step * 32;
                 cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
                 const int lead = ws.lead[gb];
@@ -527,6 +574,96 @@ __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompac
     }
 }
 
+/*
+ * The ordered sums of the sites that were scored in pieces (SEG): one warp per such site walks the site's scratch
+ * chunks in row order -- fragment chunks, then split chunks -- and replays them with the same c_replay_frag /
+ * c_replay_split as phase B of the tally kernel (lane c = chain c), so the sums are the ones the unsplit site would
+ * get (reference singlesample.py:364-378: the fp64 sums run over sorted(query_name) fragments one after another).
+ * Each lane fetches its row of the next kRD chunks (coalesced 256-byte reads of L2-resident scratch) while the
+ * chains of the current ones are replayed out of shared memory.
+ */
+constexpr int kRWarps = 4;          /* warps (= sites) per CTA */
+constexpr int kRD = 4;              /* chunks fetched ahead */
+
+template <int ASSOC>
+__global__ void __launch_bounds__(kRWarps * 32) svgt_replay_pieces_kernel(const SvgtCompactParams cp)
+{
+    const SvgtParams &p = cp.base;
+    __shared__ double s_pm[256];
+    __shared__ double s_buf[kRWarps][2][kRD][3][33];
+    __shared__ int s_lead[kRWarps][2][kRD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256; i += kRWarps * 32) s_pm[i] = p.pm[i];
+    __syncthreads();
+    const long long h = (long long)blockIdx.x * kRWarps + warp;
+    if (h >= cp.n_heavy) return;
+    const int4 hv = ldg4(cp.heavy + h);                      /* site, first scratch chunk, fragment chunks, split chunks */
+    const long long site = hv.x;
+    int nf = 0, ns = 0;
+    bool ok = site >= 0 && site < p.n_sites && hv.y >= 0 && hv.z >= 0 && hv.w >= 0 &&
+              (long long)hv.y + hv.z + hv.w <= cp.scratch_chunks;
+    if (ok) {
+        const int4 d = ldg4(cp.sites + site * 3 + 2);
+        nf = d.z; ns = d.w;
+        ok = nf >= 0 && ns >= 0 && hv.z == ((nf + 31) >> 5) && hv.w == ((ns + 31) >> 5);
+    }
+    if (!ok) {
+        if (lane == 0) { atomicCAS(p.status, 0, SVGT_ERR_ARG); atomicAdd(p.status + 2, 1); }
+        return;
+    }
+    const int cf = hv.z, T = hv.z + hv.w;
+    const double *src = cp.scratch + (long long)hv.y * 96;
+    const int *lsrc = cp.scratch_lead + hv.y;
+    double v[kRD][3];
+    int ld = 0;
+    auto fetch = [&](const int t0) {
+#pragma unroll
+        for (int i = 0; i < kRD; ++i) {
+            const bool in = t0 + i < T;
+            const double *q = src + (long long)(t0 + i) * 96;
+            v[i][0] = in ? q[lane] : 0.0; v[i][1] = in ? q[32 + lane] : 0.0; v[i][2] = in ? q[64 + lane] : 0.0;
+        }
+        ld = (lane < kRD && t0 + lane < T) ? lsrc[t0 + lane] : 0;
+    };
+    double acc = 0.0, pend = 0.0, sum_frag = 0.0;
+    fetch(0);
+    for (int t0 = 0, b = 0; t0 < T; t0 += kRD, b ^= 1) {
+#pragma unroll
+        for (int i = 0; i < kRD; ++i) {
+            s_buf[warp][b][i][0][lane] = v[i][0]; s_buf[warp][b][i][1][lane] = v[i][1]; s_buf[warp][b][i][2][lane] = v[i][2];
+        }
+        if (lane < kRD) s_lead[warp][b][lane] = ld;
+        __syncwarp();
+        if (t0 + kRD < T) fetch(t0 + kRD);
+        if (lane < 3) {
+            const int c = lane;
+            for (int i = 0; i < kRD && t0 + i < T; ++i) {
+                const int t = t0 + i;
+                const bool sp = t >= cf;
+                const int left = sp ? ns - (t - cf) * 32 : nf - t * 32;
+                const int cnt = left > 32 ? 32 : left;
+                const int lead = s_lead[warp][b][i];
+                if (!sp) c_replay_frag<ASSOC>(&s_buf[warp][b][i][c][0], &s_buf[warp][b][i][0][0], c, cnt, lead, s_pm, acc, pend);
+                else if (c < 2) c_replay_split<ASSOC>(&s_buf[warp][b][i][c + 1][0], cnt, lead, acc, pend);
+                if (t == cf - 1) {                          /* the fragment rows are done */
+                    if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+                    sum_frag = acc; acc = 0.0; pend = 0.0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 3) {
+        if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
+        const double sum_split = acc;
+        double *row = reinterpret_cast<double *>(p.out + site);
+        /* ParkedSums: ref_seq, alt_seq, alt_clip, ref_span, alt_span */
+        if (lane == 0) { row[0] = sum_frag; row[1] = sum_split; }
+        else if (lane == 1) { row[3] = sum_frag; row[2] = sum_split; }
+        else row[4] = sum_frag;
+    }
+}
+
 template <int G>
 size_t c_smem_bytes(const SvgtParams &p)
 {
@@ -537,20 +674,32 @@ size_t c_smem_bytes(const SvgtParams &p)
     return off;
 }
 
+typedef void (*CKernel)(const SvgtCompactParams);
+
+template <int G, int ASSOC>
+CKernel c_pick_kernel(bool seg)
+{
+    if constexpr (G == SVGT_C_G) {
+        if (seg) return svgt_compact_kernel<G, ASSOC, true>;
+    }
+    return svgt_compact_kernel<G, ASSOC, false>;
+}
+
 struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
 
 template <int G>
 int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, bool force_ramp = false)
 {
-    static CLaunchInfo info[2] = {};
+    static CLaunchInfo info[4] = {};
     const SvgtParams &p = cp.base;
     const int a = p.assoc_mode == SVGT_ASSOC_CLASSIC ? 1 : 0;
-    auto kern = a ? svgt_compact_kernel<G, SVGT_ASSOC_CLASSIC> : svgt_compact_kernel<G, SVGT_ASSOC_SSO>;
+    const bool seg = cp.entries != nullptr && G == SVGT_C_G;        /* a piece plan: the launch list names sites and pieces */
+    auto kern = a ? c_pick_kernel<G, SVGT_ASSOC_CLASSIC>(seg) : c_pick_kernel<G, SVGT_ASSOC_SSO>(seg);
     const size_t smem = c_smem_bytes<G>(p);
     cudaError_t e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-    CLaunchInfo &li = info[a];
+    CLaunchInfo &li = info[a + (seg ? 2 : 0)];
     const int di = dev & 15;
     if (!li.ready[di] || li.smem_set[di] < smem) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
@@ -562,7 +711,8 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, b
         li.smem_set[di] = smem; li.ready[di] = 1;
     }
     const long long cap = (long long)li.sms[di] * li.per_sm[di];      /* persistent: one resident wave */
-    const long long units = ramp ? p.n_sites : (p.n_sites + G - 1) / G;
+    const long long n_entries = seg ? cp.n_entries : p.n_sites;
+    const long long units = ramp ? n_entries : (n_entries + G - 1) / G;
     const long long want = (units + kCWarps - 1) / kCWarps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
@@ -572,11 +722,17 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, b
         const char *v = getenv("SVGT_C_RAMP_PER_WARP");
         return v && *v ? atoll(v) : (long long)SVGT_C_RAMP_PER_WARP_DEFAULT;
     }();
-    if (ramp == 1 && !force_ramp && p.n_sites >= ramp_per_warp * cap * kCWarps) ramp = 0;
+    if (ramp == 1 && !force_ramp && n_entries >= ramp_per_warp * cap * kCWarps) ramp = 0;
     SvgtCompactParams q = cp;
     q.ramp = ramp;
     kern<<<grid, SVGT_C_THREADS, smem, stream>>>(q);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    if (seg && cp.n_heavy > 0) {
+        const int rgrid = (int)((cp.n_heavy + kRWarps - 1) / kRWarps);
+        if (a) svgt_replay_pieces_kernel<SVGT_ASSOC_CLASSIC><<<rgrid, kRWarps * 32, 0, stream>>>(q);
+        else svgt_replay_pieces_kernel<SVGT_ASSOC_SSO><<<rgrid, kRWarps * 32, 0, stream>>>(q);
+        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    }
     const int cgrid = (int)((p.n_sites + 255) / 256);
     svgt_call_compact_kernel<<<cgrid, 256, 0, stream>>>(q);
     return (int)cudaGetLastError();

@@ -52,6 +52,14 @@ struct SvgtCompactParams {
     int *done_flag; int done_value; /* optional: set to done_value (system scope) once every final row is written */
     unsigned hist_max;              /* largest histogram count, 0 = unknown     */
     int ramp;
+    /* piece plan (svgt_segplan_t, include/svgt.h): sites too long for one warp are scored in pieces of whole 32-row
+     * chunks whose per-row addends go to `scratch`; svgt_replay_pieces_kernel then sums each such site in row order */
+    const int *entries; long long n_entries;    /* launch list: site index, or ~k for piece k; NULL: no plan */
+    const int4 *pieces; long long n_pieces;     /* site, first row within the site's part, rows | split << 31, scratch chunk */
+    const int4 *heavy;  long long n_heavy;      /* site, first scratch chunk, fragment chunks, split chunks */
+    double *scratch;                            /* [scratch_chunks][3][32] parked addends */
+    int *scratch_lead;                          /* [scratch_chunks] lead rows of each chunk */
+    long long scratch_chunks;
 };
 
 /* Returns a cudaError_t as int.  `grid` <= 0 lets the launcher size a persistent grid. */

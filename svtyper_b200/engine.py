@@ -74,6 +74,8 @@ class DeviceBatch(object):
         self.algorithmic_bytes = algorithmic_bytes
         self.out = None
         self.status = None
+        self.plan = None                # native.SvgtSegPlan (kept alive: desc.plan points at it), or None
+        self.plan_info = None           # {"max_chunks", "pieces", "heavy_sites", "scratch_bytes"} of that plan
 
 
 def _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode):
@@ -138,6 +140,7 @@ class Engine(object):
         self.last_h2d = self.last_d2h = 0
         self.last_kernel_ms = 0.0
         self.launches = 0                   # kernels launched through this engine
+        self.last_pieces = 0                # pieces the last score_host call cut its long sites into
 
     def close(self):
         if self._ctx:
@@ -174,6 +177,11 @@ class Engine(object):
                                 unit_mode, native.LAYOUT_SITE_ORDER if site_order else 0)
             rc = self._lib.svgt_ctx_score_host_compact(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
             launches = 2 if batch.n_sites else 0
+            npc = ctypes.c_int64()
+            self._lib.svgt_ctx_last_pieces(self._ctx, ctypes.byref(npc))
+            self.last_pieces = npc.value
+            if npc.value:
+                launches += 1               # svgt_replay_pieces_kernel
         else:
             desc = _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode)
             rc = self._lib.svgt_ctx_score_host(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
@@ -190,9 +198,11 @@ class Engine(object):
 
     # ---------------------------------------------------------------- device resident
     def upload(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
-               assoc_mode=ev.ASSOC_SSO, unit_mode=0):
+               assoc_mode=ev.ASSOC_SSO, unit_mode=0, piece_chunks=None):
         """unit_mode: 0 = pick from the batch's row counts (CompactBatch.suggest_unit_mode), else svgt_cbatch_t's
-        values (1 full units, 2 two-site units, 3 ramped units); -1 = leave the choice to the library (by site count)."""
+        values (1 full units, 2 two-site units, 3 ramped units); -1 = leave the choice to the library (by site count).
+        piece_chunks (compact batches): None = let the library plan pieces for sites too long for one warp
+        (svgt_plan_count's policy), 0 = no plan, k > 0 = pieces of at most k 32-row chunks."""
         torch = _torch()
         arrs = host_arrays(batch, split_weight, disc_weight)
         tens = {}
@@ -211,6 +221,24 @@ class Engine(object):
             desc = _descriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
                                disc_weight, assoc_mode)
         dev = DeviceBatch(tens, desc, batch.n_sites, batch.algorithmic_bytes())
+        if isinstance(batch, cp.CompactBatch) and piece_chunks != 0 and unit_mode != 2 and batch.n_sites:
+            with torch.cuda.device(self.device):    # the planner sizes pieces for this device's resident warps
+                pl = native.plan_pieces(batch.sites, min_aligned, split_slop, 0, int(piece_chunks or 0))
+            if pl is not None:
+                for k in ("entries", "pieces", "heavy"):
+                    tens["plan_" + k] = torch.from_numpy(pl[k]).to(self.device)
+                nbytes = pl["scratch_chunks"] * native.PLAN_CHUNK_BYTES
+                tens["plan_scratch"] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                sp = native.SvgtSegPlan()
+                sp.entries, sp.n_entries = tens["plan_entries"].data_ptr(), int(pl["entries"].shape[0])
+                sp.pieces, sp.n_pieces = tens["plan_pieces"].data_ptr(), int(pl["pieces"].shape[0])
+                sp.heavy, sp.n_heavy = tens["plan_heavy"].data_ptr(), int(pl["heavy"].shape[0])
+                sp.scratch, sp.scratch_chunks = tens["plan_scratch"].data_ptr(), int(pl["scratch_chunks"])
+                dev.plan = sp
+                desc.plan = ctypes.pointer(sp)
+                desc.unit_mode = 3              # heaviest entries first, one per warp
+                dev.plan_info = {"max_chunks": pl["max_chunks"], "pieces": sp.n_pieces, "heavy_sites": sp.n_heavy,
+                                 "scratch_bytes": int(nbytes)}
         dev.out = torch.zeros((max(batch.n_sites, 1), ev.OUT_BYTES), dtype=torch.uint8, device=self.device)
         dev.status = torch.zeros(4, dtype=torch.int32, device=self.device)
         return dev
@@ -230,7 +258,7 @@ class Engine(object):
                     ctypes.c_void_p(s.cuda_stream))
         native.check(rc)
         if dev.compact:
-            self.launches += 2 if dev.n_sites else 0
+            self.launches += (3 if dev.plan is not None else 2) if dev.n_sites else 0
         else:
             self.launches += self._lib.svgt_launches_per_batch(ctypes.byref(dev.desc))
         return out

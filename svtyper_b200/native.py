@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVGT_LIB") or os.path.join(HERE, "libsvgt.so")   # SVGT_LIB: A/B builds of the same ABI
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_ARG, ERR_CUDA, ERR_LOG_TABLE, ERR_LIB_INDEX, ERR_NO_DEVICE, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6
 ERR_NAMES = {ERR_ARG: "SVGT_ERR_ARG", ERR_CUDA: "SVGT_ERR_CUDA", ERR_LOG_TABLE: "SVGT_ERR_LOG_TABLE",
              ERR_LIB_INDEX: "SVGT_ERR_LIB_INDEX", ERR_NO_DEVICE: "SVGT_ERR_NO_DEVICE",
@@ -25,7 +25,9 @@ SYMBOLS = ("svgt_abi_version", "svgt_last_error", "svgt_device_count", "svgt_sco
            "svgt_launches_per_batch", "svgt_set_variant", "svgt_ctx_create", "svgt_ctx_destroy",
            "svgt_ctx_score_host", "svgt_ctx_last_traffic", "svgt_ctx_last_kernel_ms",
            "svgt_score_compact", "svgt_ctx_score_host_compact", "svgt_shared_alloc", "svgt_shared_open",
-           "svgt_shared_close", "svgt_shared_free", "svgt_wait_flags", "svgt_memcpy_d2h", "svgt_peer_copy", "svgt_set_flag")
+           "svgt_shared_close", "svgt_shared_free", "svgt_wait_flags", "svgt_memcpy_d2h", "svgt_peer_copy", "svgt_set_flag",
+           "svgt_plan_count", "svgt_plan_fill", "svgt_ctx_last_pieces")
+PLAN_CHUNK_BYTES = 784
 LAYOUT_SITE_ORDER = 1
 
 
@@ -47,6 +49,16 @@ class SvgtBatch(ctypes.Structure):
     ]
 
 
+class SvgtSegPlan(ctypes.Structure):
+    """struct svgt_segplan (include/svgt.h): the piece plan of a compact batch."""
+    _fields_ = [
+        ("entries", ctypes.c_void_p), ("n_entries", ctypes.c_int64),
+        ("pieces", ctypes.c_void_p), ("n_pieces", ctypes.c_int64),
+        ("heavy", ctypes.c_void_p), ("n_heavy", ctypes.c_int64),
+        ("scratch", ctypes.c_void_p), ("scratch_chunks", ctypes.c_int64),
+    ]
+
+
 class SvgtCBatch(ctypes.Structure):
     """struct svgt_cbatch (include/svgt.h): the compact schema."""
     _fields_ = [
@@ -65,6 +77,7 @@ class SvgtCBatch(ctypes.Structure):
         ("out_final", ctypes.c_void_p), ("done_flag", ctypes.c_void_p),
         ("done_value", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("rows_min_aligned", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("plan", ctypes.POINTER(SvgtSegPlan)),
     ]
 
 
@@ -126,6 +139,14 @@ def lib():
         L.svgt_memcpy_d2h.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.svgt_wait_flags.restype = ctypes.c_int
         L.svgt_wait_flags.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+        L.svgt_plan_count.restype = ctypes.c_int
+        L.svgt_plan_count.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)] + [ctypes.POINTER(ctypes.c_int64)] * 4
+        L.svgt_plan_fill.restype = ctypes.c_int
+        L.svgt_plan_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.svgt_ctx_last_pieces.restype = ctypes.c_int
+        L.svgt_ctx_last_pieces.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
         if L.svgt_abi_version() != ABI_VERSION:
             raise ImportError("libsvgt.so ABI %d != expected %d" % (L.svgt_abi_version(), ABI_VERSION))
         _lib = L
@@ -142,3 +163,27 @@ def set_variant(v):
     if rc < 0:
         check(rc)
     return rc
+
+
+def plan_pieces(sites, min_aligned=20, split_slop=3, resident_warps=0, force_chunks=0):
+    """svgt_plan_count + svgt_plan_fill on host site rows ([n][12] int32): None when no site is longer than a piece,
+    else dict(max_chunks, entries, pieces [n][4], heavy [n][4], scratch_chunks) -- numpy int32 arrays.
+    `resident_warps` <= 0: those of the current CUDA device (148 x 20 without one)."""
+    import numpy as np
+    L = lib()
+    sites = np.ascontiguousarray(sites, dtype=np.int32)
+    n = int(sites.shape[0])
+    mc = ctypes.c_int32()
+    ne, npc, nh, sc = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    check(L.svgt_plan_count(sites.ctypes.data, n, int(min_aligned), int(split_slop), int(resident_warps),
+                            int(force_chunks), ctypes.byref(mc), ctypes.byref(ne), ctypes.byref(npc), ctypes.byref(nh),
+                            ctypes.byref(sc)))
+    if nh.value == 0:
+        return None
+    entries = np.empty(ne.value, dtype=np.int32)
+    pieces = np.empty((npc.value, 4), dtype=np.int32)
+    heavy = np.empty((nh.value, 4), dtype=np.int32)
+    check(L.svgt_plan_fill(sites.ctypes.data, n, int(min_aligned), int(split_slop), mc.value, entries.ctypes.data,
+                           pieces.ctypes.data, heavy.ctypes.data))
+    return {"max_chunks": mc.value, "entries": entries, "pieces": pieces, "heavy": heavy,
+            "scratch_chunks": sc.value}

@@ -16,8 +16,10 @@ from util import assert_rows_match, INT_FIELDS
 pytestmark = pytest.mark.gpu
 
 # "c0" / "c1" / "c2" / "c3": compact path with work units chosen from the row counts / fixed full units / fixed
-# 2-site units / ramped units; "c9": choice left to the library (by site count); 0, 1: wide-row kernels
-PATHS = ["c0", "c1", "c2", "c3", "c9", 0, 1]
+# 2-site units / ramped units; "c9": choice left to the library (by site count) -- all without a piece plan;
+# "p1" / "p3": compact path with sites longer than 1 / 3 chunks scored in pieces (svgt_segplan_t: SEG tally kernel +
+# svgt_replay_pieces_kernel); "pa": the planner's own piece length; 0, 1: wide-row kernels
+PATHS = ["c0", "c1", "c2", "c3", "c9", "p1", "p3", "pa", 0, 1]
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +34,12 @@ def eng():
 def gpu_rows(eng, batch, path="c0", min_aligned=20, **kw):
     if isinstance(path, str):
         cb = batch if isinstance(batch, cp.CompactBatch) else cp.compact_from_wide(batch, min_aligned=min_aligned)
-        dev = eng.upload(cb, unit_mode=-1 if path == "c9" else int(path[1]), min_aligned=min_aligned, **kw)
+        if path[0] == "p":
+            dev = eng.upload(cb, min_aligned=min_aligned, piece_chunks=None if path == "pa" else int(path[1:]), **kw)
+            if path != "pa":
+                assert dev.plan is not None and dev.plan_info["pieces"] > 0, "the batch has no site to cut: nothing tested"
+        else:
+            dev = eng.upload(cb, unit_mode=-1 if path == "c9" else int(path[1]), min_aligned=min_aligned, piece_chunks=0, **kw)
     else:
         native.set_variant(path)
         dev = eng.upload(batch, min_aligned=min_aligned, **kw)
@@ -73,7 +80,7 @@ def test_hazard_vectors(eng, oracle, path):
     assert got["RS"][0] == 26 and got["RP"][0] == 12        # sequential, not tree, sums
 
 
-@pytest.mark.parametrize("path", ["c0", "c2", 0])
+@pytest.mark.parametrize("path", ["c0", "c2", "p2", 0])
 def test_classic_association_and_weights(eng, oracle, path):
     b = synth.generate("mixed100k", n_sites=3000, seed=77)
     for assoc in (ev.ASSOC_SSO, ev.ASSOC_CLASSIC):
@@ -266,6 +273,7 @@ def test_full_size_configs_against_oracle(eng, oracle):
         exp = oracle.score(b, n_threads=oracle.max_threads())
         assert_rows_match(got, exp, exact_gl=True, where="full-size " + config)
         assert gpu_rows(eng, b, "c1").tobytes() == got.tobytes()          # 8-site units only: same bytes
+        assert gpu_rows(eng, b, "pa").tobytes() == got.tobytes()          # long sites in pieces (the default upload)
 
 
 def test_stress_shape_200k_sites_against_oracle(eng, oracle):
@@ -275,6 +283,8 @@ def test_stress_shape_200k_sites_against_oracle(eng, oracle):
     got = gpu_rows(eng, b, "c0")
     exp = oracle.score(b, n_threads=oracle.max_threads())
     assert_rows_match(got, exp, exact_gl=True, where="stress1m 200k")
+    assert gpu_rows(eng, b, "pa").tobytes() == got.tobytes()              # the default upload: long sites in pieces
+    assert gpu_rows(eng, b, "p9").tobytes() == got.tobytes()
     gt = exp["GT"]
     assert (gt == ev.GT_SKIPPED).sum() > 100 and (gt == ev.GT_BLANK).sum() > 100 and (gt == ev.GT_UNDERFLOW).sum() > 100
 
@@ -349,3 +359,53 @@ def test_torch_operator_matches_engine(eng, oracle):
     torch.cuda.synchronize()
     assert int(status[0]) == 0
     assert out.cpu().numpy().reshape(-1).view(ev.OUT_DTYPE).tobytes() == ref.tobytes()
+
+
+def test_piece_plan_is_bit_identical_and_covers_the_host_path(eng, oracle, monkeypatch):
+    """A heavy-tailed batch (config stress1m: up to 10,000 reads per site) scored with its long sites cut into pieces:
+    every piece length gives the bytes of the unsplit path (and the oracle's values), through svgt_score_compact and
+    through svgt_ctx_score_host_compact (which plans by itself); pieces really were used."""
+    b = synth.generate("stress1m", n_sites=4000, seed=5)
+    cb = cp.compact_from_wide(b)
+    exp = oracle.score(b, n_threads=oracle.max_threads())
+    for assoc in (ev.ASSOC_SSO, ev.ASSOC_CLASSIC):
+        want = oracle.score(b, assoc_mode=assoc, n_threads=oracle.max_threads()) if assoc != ev.ASSOC_SSO else exp
+        base = gpu_rows(eng, cb, "c0", assoc_mode=assoc)
+        assert_rows_match(base, want, exact_gl=True, where="no plan")
+        for k in (1, 2, 7, 40, None):
+            dev = eng.upload(cb, assoc_mode=assoc, piece_chunks=k)
+            assert dev.plan is not None and dev.plan_info["heavy_sites"] > 0
+            eng.score(dev)
+            got = eng.rows(dev)
+            assert got.tobytes() == base.tobytes(), "pieces of <= %s chunks, assoc %d" % (k, assoc)
+    monkeypatch.setenv("SVGT_PLAN_FORCE_CHUNKS", "2")
+    host = eng.score_host(cb)
+    assert eng.last_pieces > 0
+    assert host.tobytes() == gpu_rows(eng, cb, "c0").tobytes()
+    monkeypatch.delenv("SVGT_PLAN_FORCE_CHUNKS")
+    host = eng.score_host(cb)                       # the planner's own choice: a 4000-site batch is cut
+    assert eng.last_pieces > 0
+    assert_rows_match(host, exp, exact_gl=True, where="host path, planned")
+
+
+def test_bad_piece_plan_is_flagged(eng):
+    """Entries / pieces that do not describe the batch raise SVGT_ERR_ARG instead of reading out of bounds."""
+    import torch
+    b = synth.generate("del10k", n_sites=500, seed=3)
+    cb = cp.compact_from_wide(b)
+    for what in ("entry", "piece_rows", "piece_scratch", "heavy"):
+        dev = eng.upload(cb, piece_chunks=1)
+        assert dev.plan is not None
+        if what == "entry":
+            dev.tensors["plan_entries"][0] = cb.n_sites + 5
+        elif what == "piece_rows":
+            dev.tensors["plan_pieces"][0, 2] = 1 << 20
+        elif what == "piece_scratch":
+            dev.tensors["plan_pieces"][0, 3] = dev.plan.scratch_chunks
+        else:
+            dev.tensors["plan_heavy"][0, 2] += 1
+        torch.cuda.synchronize()
+        eng.score(dev)
+        with pytest.raises(native.SvgtError) as ei:
+            eng.rows(dev)
+        assert ei.value.code == native.ERR_ARG, what
