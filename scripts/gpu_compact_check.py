@@ -34,7 +34,8 @@ def main():
     ap.add_argument("--no-wide", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tag", default="")
-    ap.add_argument("--pieces", default="auto", help="piece plan of the timed compact batch: auto | off | <max chunks>")
+    ap.add_argument("--pieces", default="off", help="comma list of timed variants of the compact batch, each "
+                    "<pieces>[/<early>]: piece plan auto | off | <max chunks>; call_early_rows auto | <rows> (0 = off)")
     args = ap.parse_args()
     import torch
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
@@ -114,7 +115,9 @@ def main():
     for label, batch, pc in runs:
         kw = {}
         if pc is not None:
-            kw["piece_chunks"] = None if pc == "auto" else 0 if pc == "off" else int(pc)
+            pcs, _, early = pc.partition("/")
+            kw["piece_chunks"] = None if pcs == "auto" else 0 if pcs == "off" else int(pcs)
+            kw["call_early"] = None if early in ("", "auto") else int(early)
         dev = eng.upload(batch, **kw)
         for _ in range(3):
             eng.score(dev)
@@ -130,6 +133,7 @@ def main():
         res[label] = {"ms_avg": sum(ms) / len(ms), "ms_min": min(ms)}
         if pc is not None:
             res[label].update({"pieces": pc, "plan": dev.plan_info, "unit_mode": int(dev.desc.unit_mode),
+                               "call_early_rows": int(dev.desc.call_early_rows),
                                "frac_own_B": cb.algorithmic_bytes() / (res[label]["ms_avg"] * 1e-3) / 1e9 / 6545.9,
                                "frac_survey_B": cb.survey_bytes() / (res[label]["ms_avg"] * 1e-3) / 1e9 / 6545.9})
         rows = eng.rows(dev)

@@ -118,7 +118,7 @@ __device__ __forceinline__ unsigned c_smem(const void *p) { return (unsigned)__c
 
 /* phase B of one fragment chunk for chain c: `px` = the chain's 33 parked doubles (c = 0: a + b, or the LUT
  * index pairs `pi` where a and b must be added apart); the replay of replay_frag_soa() */
-template <int ASSOC>
+template <int ASSOC, int IMASK = -1>   /* IMASK: applied to the LUT indices (the replay kernel reads them from scratch memory) */
 __device__ __forceinline__ void c_replay_frag(const double *px, const double *s, int c, int cnt, int lead, const double *s_pm,
                                               double &acc, double &pend)
 {
@@ -129,7 +129,7 @@ __device__ __forceinline__ void c_replay_frag(const double *px, const double *s,
         if (c == 0) {
             for (int j = 0; j < cnt; ++j) {
                 const int2 ix = pi[j];
-                acc = __dadd_rn(__dadd_rn(acc, s_pm[ix.x]), s_pm[ix.y]);
+                acc = __dadd_rn(__dadd_rn(acc, s_pm[ix.x & IMASK]), s_pm[ix.y & IMASK]);
             }
         } else {
 #pragma unroll 4
@@ -139,7 +139,7 @@ __device__ __forceinline__ void c_replay_frag(const double *px, const double *s,
         for (int j = 0; j < lead; ++j) {                /* rows continuing the previous chunk's last fragment */
             if (c == 0) {
                 const int2 ix = pi[j];
-                pend = __dadd_rn(__dadd_rn(pend, s_pm[ix.x]), s_pm[ix.y]);
+                pend = __dadd_rn(__dadd_rn(pend, s_pm[ix.x & IMASK]), s_pm[ix.y & IMASK]);
             } else {
                 pend = __dadd_rn(pend, px[j]);
             }
@@ -179,9 +179,21 @@ __device__ __forceinline__ void c_replay_split(const double *px, int cnt, int le
  * svgt_replay_pieces_kernel.  That takes a long site off the critical path of a small or heavy-tailed batch: its
  * chunks are scored by many warps at once, and the serial part left is one DADD per row.
  */
-template <int G, int ASSOC, bool SEG>
+/*
+ * MODE_EARLY: sites of at least cp.early_rows rows are CALLED here, by the lane that owns them, as soon as their sums
+ * are parked (c_call_early; svgt_call_compact_kernel leaves them alone).  log_choose is a chain of two dependent
+ * fp64 adds per step, up to one step per row: for the longest site of a heavy-tailed batch that is tens of
+ * microseconds which, in the call kernel, nothing overlaps.  The launch order is work-descending, so here those chains
+ * run at the start of the tally, under everything else.
+ */
+enum { MODE_PLAIN = 0, MODE_SEG = 1, MODE_EARLY = 2 };
+
+__device__ __noinline__ void c_call_early(const SvgtCompactParams &cp, const long long site, int &err);
+
+template <int G, int ASSOC, int MODE>
 __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kernel(const SvgtCompactParams cp)
 {
+    constexpr bool SEG = MODE == MODE_SEG;
     typedef CWarpSmem<G> WS;
     const SvgtParams &p = cp.base;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -513,6 +525,13 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
             }
         }
         __syncwarp();
+        if (MODE == MODE_EARLY) {                           /* long sites: the genotype call, now (their sums are parked) */
+            if (lane < G) {
+                const SiteS &S = ws.site[lane];
+                if (S.slot >= 0 && (long long)S.nf + S.ns >= cp.early_rows) c_call_early(cp, S.slot, err);
+            }
+            __syncwarp();
+        }
     }
     if (err) {
         atomicCAS(p.status, 0, err);
@@ -520,16 +539,17 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
     }
 }
 
-/* one site per thread: zeroing rules + genotype call on the parked sums (compact site rows) */
-__global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompactParams cp)
+/* zeroing rules + genotype call of one site on its parked sums (reference singlesample.py:382-473): reads the
+ * site's five sums from its row of base.out, writes the final 80-byte row (to out_final when given).
+ * `early_rows` > 0: sites of at least that many rows are called by the tally kernel itself, right after their sums
+ * (ONLY_EARLY: this is that call; otherwise such sites are left alone here) */
+template <bool ONLY_EARLY>
+__device__ __forceinline__ void c_call_one(const SvgtCompactParams &cp, const long long site, int &err)
 {
     const SvgtParams &p = cp.base;
-    const long long site = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (site >= p.n_sites) return;
     const int4 *sp = cp.sites + site * 3;
     const int4 a = ldg4(sp), b = ldg4(sp + 1), d = ldg4(sp + 2);
     const int meta = b.w;
-    int err = 0;
     svgt_out_row_t o;
     o.gl[0] = o.gl[1] = o.gl[2] = 0.0; o.sq = 0.0;
     o.gt = 0; o.gq = 0; o.dp = 0; o.ro = 0; o.ao = 0; o.qr = 0; o.qa = 0;
@@ -541,6 +561,7 @@ __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompac
         ParkedSums s = {0.0, 0.0, 0.0, 0.0, 0.0};
         const long long roff = ((long long)(unsigned)d.x) | ((long long)d.y << 32);
         const bool ok = !(d.z < 0 || d.w < 0 || roff < 0 || roff + d.z + d.w > cp.n_rows);
+        if (!ONLY_EARLY && ok && cp.early_rows > 0 && (long long)d.z + d.w >= cp.early_rows) return;   /* called by the tally kernel */
         if (ok && (d.z > 0 || d.w > 0)) {
             const double *row = reinterpret_cast<const double *>(p.out + site);
             s.ref_seq = row[0]; s.alt_seq = row[1]; s.alt_clip = row[2]; s.ref_span = row[3]; s.alt_span = row[4];
@@ -554,6 +575,24 @@ __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompac
     const int4 *src = reinterpret_cast<const int4 *>(&o);
 #pragma unroll
     for (int i = 0; i < 5; ++i) dst[i] = src[i];
+}
+
+__device__ __noinline__ void c_call_early(const SvgtCompactParams &cp, const long long site, int &err)
+{
+    c_call_one<true>(cp, site, err);
+}
+
+/* one site per thread, in launch order when there is one (work-descending: the long log_choose chains -- two
+ * dependent fp64 adds per step, statistics.py:9-20 -- start first and share their warps with chains of similar length) */
+__global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompactParams cp)
+{
+    const SvgtParams &p = cp.base;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int err = 0;
+    if (idx < p.n_sites) {
+        long long site = p.order ? (long long)p.order[idx] : idx;
+        if (site >= 0 && site < p.n_sites) c_call_one<false>(cp, site, err);     /* a bad entry was flagged by the tally kernel */
+    }
     if (err) {
         atomicCAS(p.status, 0, err);
         atomicAdd(p.status + 2, 1);
@@ -643,7 +682,7 @@ __global__ void __launch_bounds__(kRWarps * 32) svgt_replay_pieces_kernel(const 
                 const int left = sp ? ns - (t - cf) * 32 : nf - t * 32;
                 const int cnt = left > 32 ? 32 : left;
                 const int lead = s_lead[warp][b][i];
-                if (!sp) c_replay_frag<ASSOC>(&s_buf[warp][b][i][c][0], &s_buf[warp][b][i][0][0], c, cnt, lead, s_pm, acc, pend);
+                if (!sp) c_replay_frag<ASSOC, 255>(&s_buf[warp][b][i][c][0], &s_buf[warp][b][i][0][0], c, cnt, lead, s_pm, acc, pend);
                 else if (c < 2) c_replay_split<ASSOC>(&s_buf[warp][b][i][c + 1][0], cnt, lead, acc, pend);
                 if (t == cf - 1) {                          /* the fragment rows are done */
                     if (ASSOC == SVGT_ASSOC_SSO) acc = __dadd_rn(acc, pend);
@@ -677,12 +716,13 @@ size_t c_smem_bytes(const SvgtParams &p)
 typedef void (*CKernel)(const SvgtCompactParams);
 
 template <int G, int ASSOC>
-CKernel c_pick_kernel(bool seg)
+CKernel c_pick_kernel(int mode)
 {
     if constexpr (G == SVGT_C_G) {
-        if (seg) return svgt_compact_kernel<G, ASSOC, true>;
+        if (mode == MODE_SEG) return svgt_compact_kernel<G, ASSOC, MODE_SEG>;
+        if (mode == MODE_EARLY) return svgt_compact_kernel<G, ASSOC, MODE_EARLY>;
     }
-    return svgt_compact_kernel<G, ASSOC, false>;
+    return svgt_compact_kernel<G, ASSOC, MODE_PLAIN>;
 }
 
 struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
@@ -690,16 +730,17 @@ struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set
 template <int G>
 int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, bool force_ramp = false)
 {
-    static CLaunchInfo info[4] = {};
+    static CLaunchInfo info[6] = {};
     const SvgtParams &p = cp.base;
     const int a = p.assoc_mode == SVGT_ASSOC_CLASSIC ? 1 : 0;
     const bool seg = cp.entries != nullptr && G == SVGT_C_G;        /* a piece plan: the launch list names sites and pieces */
-    auto kern = a ? c_pick_kernel<G, SVGT_ASSOC_CLASSIC>(seg) : c_pick_kernel<G, SVGT_ASSOC_SSO>(seg);
+    const int mode = seg ? MODE_SEG : (cp.early_rows > 0 && G == SVGT_C_G) ? MODE_EARLY : MODE_PLAIN;
+    auto kern = a ? c_pick_kernel<G, SVGT_ASSOC_CLASSIC>(mode) : c_pick_kernel<G, SVGT_ASSOC_SSO>(mode);
     const size_t smem = c_smem_bytes<G>(p);
     cudaError_t e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-    CLaunchInfo &li = info[a + (seg ? 2 : 0)];
+    CLaunchInfo &li = info[a + 2 * mode];
     const int di = dev & 15;
     if (!li.ready[di] || li.smem_set[di] < smem) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
@@ -725,6 +766,7 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, b
     if (ramp == 1 && !force_ramp && n_entries >= ramp_per_warp * cap * kCWarps) ramp = 0;
     SvgtCompactParams q = cp;
     q.ramp = ramp;
+    if (mode != MODE_EARLY) q.early_rows = 0;               /* the call kernel then calls every site */
     kern<<<grid, SVGT_C_THREADS, smem, stream>>>(q);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     if (seg && cp.n_heavy > 0) {
