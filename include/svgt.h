@@ -148,11 +148,7 @@ typedef struct svgt_cbatch {
     int32_t flags;                            /* SVGT_LAYOUT_*                           */
     int32_t rows_min_aligned;                 /* the -m the packer evaluated the MULTI rows' is_ref_seq bits
                                                  with; must equal min_aligned (SVGT_ERR_ARG otherwise)     */
-    int32_t call_early_rows;                  /* > 0: sites with at least this many evidence rows get their genotype call
-                                                 from the tally kernel, right after their sums, instead of from the call
-                                                 kernel -- the long log_choose chains (two dependent fp64 adds per step,
-                                                 statistics.py:9-20) of a heavy-tailed batch then run under the rest of
-                                                 the tally.  Same results.  0: off.  Ignored with a plan.            */
+    int32_t reserved;
     const svgt_segplan_t *plan;               /* optional piece plan (host struct, device pointers inside); with a
                                                  plan `order` is not used: plan->entries is the launch list   */
 } svgt_cbatch_t;
@@ -184,10 +180,6 @@ int svgt_plan_count(const int32_t *sites_host, int64_t n_sites, int32_t min_alig
                     int64_t *n_pieces, int64_t *n_heavy, int64_t *scratch_chunks);
 int svgt_plan_fill(const int32_t *sites_host, int64_t n_sites, int32_t min_aligned, int32_t split_slop,
                    int32_t max_chunks, int32_t *entries, int32_t *pieces, int32_t *heavy);
-
-/* svgt_cbatch_t::call_early_rows worth using for these HOST site rows: 0 unless the longest site's log_choose chain
- * would be a noticeable share (> ~5 %) of the batch's run time, else a quarter of the longest site's rows (>= 256). */
-int32_t svgt_suggest_call_early(const int32_t *sites_host, int64_t n_sites);
 
 /* Number of kernel launches svgt_score_batch issues for this batch (bench bookkeeping). */
 int svgt_launches_per_batch(const svgt_batch_t *batch);

@@ -35,7 +35,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tag", default="")
     ap.add_argument("--pieces", default="off", help="comma list of timed variants of the compact batch, each "
-                    "<pieces>[/<early>]: piece plan auto | off | <max chunks>; call_early_rows auto | <rows> (0 = off)")
+                    "<pieces>[/<unit_mode>]: piece plan auto | off | <max chunks>; unit_mode used with the plan (1 full units, 3 ramp)")
     args = ap.parse_args()
     import torch
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
@@ -115,9 +115,10 @@ def main():
     for label, batch, pc in runs:
         kw = {}
         if pc is not None:
-            pcs, _, early = pc.partition("/")
+            pcs, _, um = pc.partition("/")
             kw["piece_chunks"] = None if pcs == "auto" else 0 if pcs == "off" else int(pcs)
-            kw["call_early"] = None if early in ("", "auto") else int(early)
+            if um:
+                kw["piece_unit_mode"] = int(um)
         dev = eng.upload(batch, **kw)
         for _ in range(3):
             eng.score(dev)
@@ -133,7 +134,6 @@ def main():
         res[label] = {"ms_avg": sum(ms) / len(ms), "ms_min": min(ms)}
         if pc is not None:
             res[label].update({"pieces": pc, "plan": dev.plan_info, "unit_mode": int(dev.desc.unit_mode),
-                               "call_early_rows": int(dev.desc.call_early_rows),
                                "frac_own_B": cb.algorithmic_bytes() / (res[label]["ms_avg"] * 1e-3) / 1e9 / 6545.9,
                                "frac_survey_B": cb.survey_bytes() / (res[label]["ms_avg"] * 1e-3) / 1e9 / 6545.9})
         rows = eng.rows(dev)

@@ -366,7 +366,6 @@ int svgt_score_compact(const svgt_cbatch_t *b, void *out_rows, int32_t *status, 
     cp.out_final = (svgt_out_row_t *)b->out_final;
     cp.done_flag = b->done_flag; cp.done_value = b->done_value;
     cp.hist_max = b->hist_max;
-    cp.early_rows = b->call_early_rows > 0 && !(b->plan && b->plan->n_heavy > 0) && b->unit_mode != 2 ? b->call_early_rows : 0;
     if (b->plan && b->plan->n_heavy > 0) {
         const svgt_segplan_t *pl = b->plan;
         if (pl->n_entries < 0 || pl->n_pieces < 0 || pl->scratch_chunks < 0 || !pl->entries || !pl->pieces || !pl->heavy ||
@@ -460,25 +459,6 @@ extern "C" int svgt_plan_count(const int32_t *sites, int64_t n_sites, int32_t mi
     if (np >= 0x7fffffffLL || sc >= 0x7fffffffLL || ne >= 0x7fffffffLL) return fail(SVGT_ERR_ARG, "too many %s", "pieces");
     *n_entries = ne; *n_pieces = np; *n_heavy = nh; *scratch_chunks = sc;
     return SVGT_OK;
-}
-
-/* svgt_cbatch_t::call_early_rows for a batch (see include/svgt.h) */
-extern "C" int32_t svgt_suggest_call_early(const int32_t *sites, int64_t n_sites)
-{
-    if (n_sites <= 0 || !sites) return 0;
-    int64_t total = 0, longest = 0;
-    for (int64_t i = 0; i < n_sites; ++i) {
-        const int32_t *row = sites + i * SVGT_CSITE_WORDS;
-        if ((row[7] & (1 << 4)) || row[10] < 0 || row[11] < 0) continue;
-        const int64_t r = (int64_t)row[10] + row[11];
-        total += r;
-        if (r > longest) longest = r;
-    }
-    /* the longest site's log_choose chain: up to one step of two dependent fp64 adds (~90 cycles, 46 ns) per row;
-     * the batch: ~105 rows per ns.  Worth overlapping once the chain exceeds 5 % of the batch. */
-    if (longest * 96600 <= total) return 0;
-    const int64_t t = longest / 4 > 256 ? longest / 4 : 256;
-    return (int32_t)(t > 0x7fffffff ? 0x7fffffff : t);
 }
 
 extern "C" int svgt_plan_fill(const int32_t *sites, int64_t n_sites, int32_t min_aligned, int32_t split_slop,

@@ -179,21 +179,9 @@ __device__ __forceinline__ void c_replay_split(const double *px, int cnt, int le
  * svgt_replay_pieces_kernel.  That takes a long site off the critical path of a small or heavy-tailed batch: its
  * chunks are scored by many warps at once, and the serial part left is one DADD per row.
  */
-/*
- * MODE_EARLY: sites of at least cp.early_rows rows are CALLED here, by the lane that owns them, as soon as their sums
- * are parked (c_call_early; svgt_call_compact_kernel leaves them alone).  log_choose is a chain of two dependent
- * fp64 adds per step, up to one step per row: for the longest site of a heavy-tailed batch that is tens of
- * microseconds which, in the call kernel, nothing overlaps.  The launch order is work-descending, so here those chains
- * run at the start of the tally, under everything else.
- */
-enum { MODE_PLAIN = 0, MODE_SEG = 1, MODE_EARLY = 2 };
-
-__device__ __noinline__ void c_call_early(const SvgtCompactParams &cp, const long long site, int &err);
-
-template <int G, int ASSOC, int MODE>
+template <int G, int ASSOC, bool SEG>
 __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kernel(const SvgtCompactParams cp)
 {
-    constexpr bool SEG = MODE == MODE_SEG;
     typedef CWarpSmem<G> WS;
     const SvgtParams &p = cp.base;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -525,13 +513,6 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
             }
         }
         __syncwarp();
-        if (MODE == MODE_EARLY) {                           /* long sites: the genotype call, now (their sums are parked) */
-            if (lane < G) {
-                const SiteS &S = ws.site[lane];
-                if (S.slot >= 0 && (long long)S.nf + S.ns >= cp.early_rows) c_call_early(cp, S.slot, err);
-            }
-            __syncwarp();
-        }
     }
     if (err) {
         atomicCAS(p.status, 0, err);
@@ -541,9 +522,8 @@ __global__ void __launch_bounds__(SVGT_C_THREADS, SVGT_C_MINB) svgt_compact_kern
 
 /* zeroing rules + genotype call of one site on its parked sums (reference singlesample.py:382-473): reads the
  * site's five sums from its row of base.out, writes the final 80-byte row (to out_final when given).
- * `early_rows` > 0: sites of at least that many rows are called by the tally kernel itself, right after their sums
- * (ONLY_EARLY: this is that call; otherwise such sites are left alone here) */
-template <bool ONLY_EARLY>
+ */
+template <bool PIPE>
 __device__ __forceinline__ void c_call_one(const SvgtCompactParams &cp, const long long site, int &err)
 {
     const SvgtParams &p = cp.base;
@@ -561,7 +541,6 @@ __device__ __forceinline__ void c_call_one(const SvgtCompactParams &cp, const lo
         ParkedSums s = {0.0, 0.0, 0.0, 0.0, 0.0};
         const long long roff = ((long long)(unsigned)d.x) | ((long long)d.y << 32);
         const bool ok = !(d.z < 0 || d.w < 0 || roff < 0 || roff + d.z + d.w > cp.n_rows);
-        if (!ONLY_EARLY && ok && cp.early_rows > 0 && (long long)d.z + d.w >= cp.early_rows) return;   /* called by the tally kernel */
         if (ok && (d.z > 0 || d.w > 0)) {
             const double *row = reinterpret_cast<const double *>(p.out + site);
             s.ref_seq = row[0]; s.alt_seq = row[1]; s.alt_clip = row[2]; s.ref_span = row[3]; s.alt_span = row[4];
@@ -569,7 +548,7 @@ __device__ __forceinline__ void c_call_one(const SvgtCompactParams &cp, const lo
         Tables t;
         t.pm = p.pm; t.libs = nullptr; t.hist = p.hist;
         t.conc = 0.0; t.disc = 0.0;
-        call_site(p, t, meta & 3, s.ref_seq, s.alt_seq, s.alt_clip, s.ref_span, s.alt_span, o, err);
+        call_site<PIPE>(p, t, meta & 3, s.ref_seq, s.alt_seq, s.alt_clip, s.ref_span, s.alt_span, o, err);
     }
     int4 *dst = reinterpret_cast<int4 *>((cp.out_final ? cp.out_final : p.out) + site);
     const int4 *src = reinterpret_cast<const int4 *>(&o);
@@ -577,21 +556,23 @@ __device__ __forceinline__ void c_call_one(const SvgtCompactParams &cp, const lo
     for (int i = 0; i < 5; ++i) dst[i] = src[i];
 }
 
-__device__ __noinline__ void c_call_early(const SvgtCompactParams &cp, const long long site, int &err)
-{
-    c_call_one<true>(cp, site, err);
-}
+/* one site per thread.  SMALL (batches of up to kCallSmallMax sites, where the longest log_choose chain -- two
+ * dependent fp64 adds per step, statistics.py:9-20 -- is a visible share of the step): the sites are walked in launch
+ * order when there is one (work-descending: the long chains start first and share their warps with chains of similar
+ * length; -10 % on the 10k-site shape) and the chain's LUT values are fetched ahead.  Larger batches keep the index
+ * order, whose coalesced site rows matter more (+0.8 % at 1M sites otherwise), and the leaner loop (fewer registers:
+ * more resident threads) */
+constexpr long long kCallSmallMax = 1 << 18;
 
-/* one site per thread, in launch order when there is one (work-descending: the long log_choose chains -- two
- * dependent fp64 adds per step, statistics.py:9-20 -- start first and share their warps with chains of similar length) */
+template <bool SMALL>
 __global__ void __launch_bounds__(256) svgt_call_compact_kernel(const SvgtCompactParams cp)
 {
     const SvgtParams &p = cp.base;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int err = 0;
     if (idx < p.n_sites) {
-        long long site = p.order ? (long long)p.order[idx] : idx;
-        if (site >= 0 && site < p.n_sites) c_call_one<false>(cp, site, err);     /* a bad entry was flagged by the tally kernel */
+        const long long site = (SMALL && p.order) ? (long long)p.order[idx] : idx;
+        if (site >= 0 && site < p.n_sites) c_call_one<SMALL>(cp, site, err);     /* a bad entry was flagged by the tally kernel */
     }
     if (err) {
         atomicCAS(p.status, 0, err);
@@ -716,13 +697,12 @@ size_t c_smem_bytes(const SvgtParams &p)
 typedef void (*CKernel)(const SvgtCompactParams);
 
 template <int G, int ASSOC>
-CKernel c_pick_kernel(int mode)
+CKernel c_pick_kernel(bool seg)
 {
     if constexpr (G == SVGT_C_G) {
-        if (mode == MODE_SEG) return svgt_compact_kernel<G, ASSOC, MODE_SEG>;
-        if (mode == MODE_EARLY) return svgt_compact_kernel<G, ASSOC, MODE_EARLY>;
+        if (seg) return svgt_compact_kernel<G, ASSOC, true>;
     }
-    return svgt_compact_kernel<G, ASSOC, MODE_PLAIN>;
+    return svgt_compact_kernel<G, ASSOC, false>;
 }
 
 struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set[16]; };
@@ -730,17 +710,16 @@ struct CLaunchInfo { int ready[16]; int per_sm[16]; int sms[16]; size_t smem_set
 template <int G>
 int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, bool force_ramp = false)
 {
-    static CLaunchInfo info[6] = {};
+    static CLaunchInfo info[4] = {};
     const SvgtParams &p = cp.base;
     const int a = p.assoc_mode == SVGT_ASSOC_CLASSIC ? 1 : 0;
     const bool seg = cp.entries != nullptr && G == SVGT_C_G;        /* a piece plan: the launch list names sites and pieces */
-    const int mode = seg ? MODE_SEG : (cp.early_rows > 0 && G == SVGT_C_G) ? MODE_EARLY : MODE_PLAIN;
-    auto kern = a ? c_pick_kernel<G, SVGT_ASSOC_CLASSIC>(mode) : c_pick_kernel<G, SVGT_ASSOC_SSO>(mode);
+    auto kern = a ? c_pick_kernel<G, SVGT_ASSOC_CLASSIC>(seg) : c_pick_kernel<G, SVGT_ASSOC_SSO>(seg);
     const size_t smem = c_smem_bytes<G>(p);
     cudaError_t e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
-    CLaunchInfo &li = info[a + 2 * mode];
+    CLaunchInfo &li = info[a + (seg ? 2 : 0)];
     const int di = dev & 15;
     if (!li.ready[di] || li.smem_set[di] < smem) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
@@ -766,7 +745,6 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, b
     if (ramp == 1 && !force_ramp && n_entries >= ramp_per_warp * cap * kCWarps) ramp = 0;
     SvgtCompactParams q = cp;
     q.ramp = ramp;
-    if (mode != MODE_EARLY) q.early_rows = 0;               /* the call kernel then calls every site */
     kern<<<grid, SVGT_C_THREADS, smem, stream>>>(q);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     if (seg && cp.n_heavy > 0) {
@@ -776,7 +754,8 @@ int launch_compact(const SvgtCompactParams &cp, int ramp, cudaStream_t stream, b
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     }
     const int cgrid = (int)((p.n_sites + 255) / 256);
-    svgt_call_compact_kernel<<<cgrid, 256, 0, stream>>>(q);
+    if (p.n_sites <= kCallSmallMax) svgt_call_compact_kernel<true><<<cgrid, 256, 0, stream>>>(q);
+    else svgt_call_compact_kernel<false><<<cgrid, 256, 0, stream>>>(q);
     return (int)cudaGetLastError();
 }
 

@@ -290,6 +290,7 @@ __device__ __forceinline__ void split_row(const Tables &t, const SplitK &k, cons
 }
 
 /* ---------------- genotype call, singlesample.py:382-473 + statistics.py:9-37 ---------------- */
+template <bool PIPE = false>   /* PIPE: log_choose's LUT values are fetched eight steps ahead (32 more registers) */
 __device__ __forceinline__ void call_site(const SvgtParams &p, const Tables &t, int svtype, double ref_seq,
                                           double alt_seq, double alt_clip, double ref_span, double alt_span,
                                           svgt_out_row_t &o, int &err)
@@ -318,9 +319,30 @@ __device__ __forceinline__ void call_site(const SvgtParams &p, const Tables &t, 
     if (k * 2 > n) k = n - k;
     double lc = 0.0;
     {
+        /* r += log(n, 10); r -= log(d, 10); n -= 1 (statistics.py:14-18): 2 k dependent fp64 adds (8 cycles each on a
+         * B200, scripts/ub/ub_fp64_latency.cu); the only freedom is when the LUT values are fetched -- eight steps
+         * ahead of the adds that use them, so the chain never waits for a load */
         const double *ln = p.logt + n;
         const double *ld = p.logt + 1;
-        for (long long d = 0; d < k; ++d) {
+        long long d = 0;
+        if (PIPE && k >= 16) {
+            double a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = __ldg(ln - i); b[i] = __ldg(ld + i); }
+            for (; d + 16 <= k; d += 8) {
+                double na[8], nb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { na[i] = __ldg(ln - (d + 8 + i)); nb[i] = __ldg(ld + (d + 8 + i)); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { lc = __dadd_rn(lc, a[i]); lc = __dsub_rn(lc, b[i]); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a[i] = na[i]; b[i] = nb[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { lc = __dadd_rn(lc, a[i]); lc = __dsub_rn(lc, b[i]); }
+            d += 8;
+        }
+        for (; d < k; ++d) {
             lc = __dadd_rn(lc, __ldg(ln - d));
             lc = __dsub_rn(lc, __ldg(ld + d));
         }

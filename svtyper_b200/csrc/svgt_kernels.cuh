@@ -60,7 +60,6 @@ struct SvgtCompactParams {
     double *scratch;                            /* [scratch_chunks][3][32] parked addends */
     int *scratch_lead;                          /* [scratch_chunks] lead rows of each chunk */
     long long scratch_chunks;
-    long long early_rows;                       /* > 0: sites of at least this many rows are called by the tally kernel */
 };
 
 /* Returns a cudaError_t as int.  `grid` <= 0 lets the launcher size a persistent grid. */

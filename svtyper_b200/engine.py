@@ -92,16 +92,8 @@ def _descriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_w
     return d
 
 
-def suggest_call_early(batch):
-    """svgt_cbatch_t.call_early_rows for a CompactBatch (the library's policy, svgt_suggest_call_early)."""
-    if batch.n_sites == 0:
-        return 0
-    sites = np.ascontiguousarray(batch.sites, dtype=np.int32)
-    return int(native.lib().svgt_suggest_call_early(sites.ctypes.data, int(sites.shape[0])))
-
-
 def _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode,
-                 unit_mode=0, flags=0, call_early=None):
+                 unit_mode=0, flags=0):
     d = native.SvgtCBatch()
     d.sites, d.n_sites = ptr["sites"], batch.n_sites
     d.rows, d.n_rows = ptr["rows"], batch.n_rows
@@ -115,7 +107,6 @@ def _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_
     d.split_weight, d.disc_weight = float(split_weight), float(disc_weight)
     d.flags = int(flags)
     d.rows_min_aligned = int(batch.min_aligned)
-    d.call_early_rows = suggest_call_early(batch) if call_early is None else int(call_early)
     return d
 
 
@@ -164,7 +155,7 @@ class Engine(object):
 
     # ---------------------------------------------------------------- host buffers in/out
     def score_host(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
-                   assoc_mode=ev.ASSOC_SSO, arrays=None, out=None, site_order=True, unit_mode=0, call_early=None):
+                   assoc_mode=ev.ASSOC_SSO, arrays=None, out=None, site_order=True, unit_mode=0):
         """Score a host batch (CompactBatch: the default path; EvidenceBatch: wide rows, the
         compatibility entry); returns OUT_DTYPE rows (numpy).
 
@@ -183,7 +174,7 @@ class Engine(object):
             if unit_mode == 0:
                 unit_mode = batch.suggest_unit_mode()
             desc = _cdescriptor(ptr, batch, n_log, min_aligned, split_slop, split_weight, disc_weight, assoc_mode,
-                                unit_mode, native.LAYOUT_SITE_ORDER if site_order else 0, call_early)
+                                unit_mode, native.LAYOUT_SITE_ORDER if site_order else 0)
             rc = self._lib.svgt_ctx_score_host_compact(self._ctx, ctypes.byref(desc), ctypes.c_void_p(optr))
             launches = 2 if batch.n_sites else 0
             npc = ctypes.c_int64()
@@ -207,14 +198,13 @@ class Engine(object):
 
     # ---------------------------------------------------------------- device resident
     def upload(self, batch, min_aligned=20, split_slop=3, split_weight=1.0, disc_weight=1.0,
-               assoc_mode=ev.ASSOC_SSO, unit_mode=0, piece_chunks=0, call_early=None):
+               assoc_mode=ev.ASSOC_SSO, unit_mode=0, piece_chunks=0, piece_unit_mode=1):
         """unit_mode: 0 = pick from the batch's row counts (CompactBatch.suggest_unit_mode), else svgt_cbatch_t's
         values (1 full units, 2 two-site units, 3 ramped units); -1 = leave the choice to the library (by site count).
         piece_chunks (compact batches): 0 = no piece plan (the default: measured, a plan does not pay on any shape
         of BASELINE.json -- profiles/README.md), None = let the library plan pieces for sites too long for one warp
-        (svgt_plan_count's policy), k > 0 = pieces of at most k 32-row chunks.
-        call_early (compact batches): svgt_cbatch_t.call_early_rows; None = the library's policy
-        (svgt_suggest_call_early), 0 = off."""
+        (svgt_plan_count's policy), k > 0 = pieces of at most k 32-row chunks; piece_unit_mode: the unit_mode used
+        with a plan (1: full 6-entry units -- no entry is longer than a piece, so there is no tail to ramp for)."""
         torch = _torch()
         arrs = host_arrays(batch, split_weight, disc_weight)
         tens = {}
@@ -228,7 +218,7 @@ class Engine(object):
             if unit_mode == 0:                      # auto: decided from the sites' row counts (we have them here)
                 unit_mode = batch.suggest_unit_mode()
             desc = _cdescriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
-                                disc_weight, assoc_mode, unit_mode, native.LAYOUT_SITE_ORDER, call_early)
+                                disc_weight, assoc_mode, unit_mode, native.LAYOUT_SITE_ORDER)
         else:
             desc = _descriptor(ptr, batch, arrs["logt"].size, min_aligned, split_slop, split_weight,
                                disc_weight, assoc_mode)
@@ -248,7 +238,7 @@ class Engine(object):
                 sp.scratch, sp.scratch_chunks = tens["plan_scratch"].data_ptr(), int(pl["scratch_chunks"])
                 dev.plan = sp
                 desc.plan = ctypes.pointer(sp)
-                desc.unit_mode = 3              # heaviest entries first, one per warp
+                desc.unit_mode = int(piece_unit_mode)
                 dev.plan_info = {"max_chunks": pl["max_chunks"], "pieces": sp.n_pieces, "heavy_sites": sp.n_heavy,
                                  "scratch_bytes": int(nbytes)}
         dev.out = torch.zeros((max(batch.n_sites, 1), ev.OUT_BYTES), dtype=torch.uint8, device=self.device)

@@ -26,7 +26,7 @@ SYMBOLS = ("svgt_abi_version", "svgt_last_error", "svgt_device_count", "svgt_sco
            "svgt_ctx_score_host", "svgt_ctx_last_traffic", "svgt_ctx_last_kernel_ms",
            "svgt_score_compact", "svgt_ctx_score_host_compact", "svgt_shared_alloc", "svgt_shared_open",
            "svgt_shared_close", "svgt_shared_free", "svgt_wait_flags", "svgt_memcpy_d2h", "svgt_peer_copy", "svgt_set_flag",
-           "svgt_plan_count", "svgt_plan_fill", "svgt_ctx_last_pieces", "svgt_suggest_call_early")
+           "svgt_plan_count", "svgt_plan_fill", "svgt_ctx_last_pieces")
 PLAN_CHUNK_BYTES = 784
 LAYOUT_SITE_ORDER = 1
 
@@ -76,7 +76,7 @@ class SvgtCBatch(ctypes.Structure):
         ("split_weight", ctypes.c_double), ("disc_weight", ctypes.c_double),
         ("out_final", ctypes.c_void_p), ("done_flag", ctypes.c_void_p),
         ("done_value", ctypes.c_int32), ("flags", ctypes.c_int32),
-        ("rows_min_aligned", ctypes.c_int32), ("call_early_rows", ctypes.c_int32),
+        ("rows_min_aligned", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("plan", ctypes.POINTER(SvgtSegPlan)),
     ]
 
@@ -145,8 +145,6 @@ def lib():
         L.svgt_plan_fill.restype = ctypes.c_int
         L.svgt_plan_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-        L.svgt_suggest_call_early.restype = ctypes.c_int32
-        L.svgt_suggest_call_early.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         L.svgt_ctx_last_pieces.restype = ctypes.c_int
         L.svgt_ctx_last_pieces.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
         if L.svgt_abi_version() != ABI_VERSION:

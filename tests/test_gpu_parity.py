@@ -388,26 +388,6 @@ def test_piece_plan_is_bit_identical_and_covers_the_host_path(eng, oracle, monke
     assert_rows_match(host, exp, exact_gl=True, where="host path")
 
 
-def test_early_call_is_bit_identical(eng, oracle):
-    """Long sites called by the tally kernel (svgt_cbatch_t.call_early_rows) instead of the call kernel: same bytes
-    for every threshold, both association orders, with and without a launch order, through both entry points."""
-    b = synth.generate("stress1m", n_sites=4000, seed=6)
-    cb = cp.compact_from_wide(b)
-    from svtyper_b200 import engine
-    assert engine.suggest_call_early(cb) >= 256             # a 4000-site heavy-tailed batch: the policy turns it on
-    for assoc in (ev.ASSOC_SSO, ev.ASSOC_CLASSIC):
-        exp = oracle.score(b, assoc_mode=assoc, n_threads=oracle.max_threads())
-        base = gpu_rows(eng, cb, "c0", assoc_mode=assoc, call_early=0)
-        assert_rows_match(base, exp, exact_gl=True, where="early off")
-        for rows in (1, 40, 300, 5000, 1 << 30, None):
-            for path in ("c0", "c1", "c3"):
-                got = gpu_rows(eng, cb, path, assoc_mode=assoc, call_early=rows)
-                assert got.tobytes() == base.tobytes(), "call_early_rows %s path %s assoc %d" % (rows, path, assoc)
-    plain = cp.CompactBatch(cb.sites, cb.rows, cb.libs, order=None)
-    assert gpu_rows(eng, plain, "c1", call_early=64).tobytes() == gpu_rows(eng, cb, "c0", call_early=0).tobytes()
-    assert eng.score_host(cb, call_early=100).tobytes() == eng.score_host(cb, call_early=0).tobytes()
-
-
 def test_bad_piece_plan_is_flagged(eng):
     """Entries / pieces that do not describe the batch raise SVGT_ERR_ARG instead of reading out of bounds."""
     import torch
