@@ -12,5 +12,6 @@ setup(
     package_data={"svtyper_b200": ["*.so", "csrc/*"]},
     python_requires=">=3.9",
     install_requires=["numpy"],
-    entry_points={"console_scripts": ["svtyper=svtyper_b200.classic:cli", "svtyper-sso=svtyper_b200.singlesample:cli"]},
+    entry_points={"console_scripts": ["svtyper=svtyper_b200.classic:cli", "svtyper-sso=svtyper_b200.singlesample:cli",
+                                      "svtyper-paste=svtyper_b200.vcf_paste:cli"]},
 )

@@ -107,19 +107,20 @@ class CompactBatch(object):
         """Site permutation bucketing warps by work (descending rows)."""
         return np.argsort(-self.work(), kind="stable").astype(np.int32)
 
-    def suggest_unit_mode(self, resident_warps=148 * 20, unit_sites=6) -> int:
+    def suggest_unit_mode(self, resident_warps=148 * 20, unit_sites=6, margin=1.5) -> int:
         """svgt_cbatch_t.unit_mode for this batch: ramped work units (3) iff the heaviest unit -- the
-        `unit_sites` largest sites, which the work-descending launch order puts on one warp -- outweighs a warp's
-        fair share of the batch (then it is the critical path: measured -8 % on the heavy-tailed stress shape at
-        200k sites, -27 % at 10k sites); full units (1) otherwise (the ramp costs 7-9 % on 125k-500k evenly
-        sized sites).  Identity launch order (no `order`): the ramp has nothing sorted to spread -> 1."""
+        `unit_sites` largest sites, which the work-descending launch order puts on one warp -- outweighs `margin`
+        times a warp's fair share of the batch (then it is the critical path: measured -8 % on the heavy-tailed
+        stress shape at 200k sites, ratio 1.65; -2 % on mixed100k, ratio 1.58; -27 % at 10k sites); full units (1)
+        otherwise (the ramp costs 7-9 % on 125k-500k evenly sized sites; at 125k sites of the benchmark shape the
+        ratio is 1.09).  Identity launch order (no `order`): the ramp has nothing sorted to spread -> 1."""
         if self.order is None or self.n_sites == 0:
             return 1
         w = self.work()
         k = min(unit_sites, w.shape[0])
         heaviest = int(np.partition(w, w.shape[0] - k)[-k:].sum())
         fair = float(w.sum()) / max(resident_warps, 1)
-        return 3 if heaviest > fair else 1
+        return 3 if heaviest > margin * fair else 1
 
     def log_table_size(self, split_weight=1.0, disc_weight=1.0) -> int:
         if self.n_sites == 0:

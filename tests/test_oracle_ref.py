@@ -20,8 +20,8 @@ def ref():
     return ref_loader.load()
 
 
-@pytest.mark.parametrize("config,n", [("del10k", 150), ("mixed100k", 200), ("del1m4lib", 150),
-                                      ("stress1m", 120)])
+@pytest.mark.parametrize("config,n", [("del10k", 600), ("mixed100k", 800), ("del1m4lib", 600),
+                                      ("stress1m", 500)])
 def test_oracle_vs_live_reference(oracle, ref, config, n):
     from oracle import ref_adapter
     b = synth.generate(config, n_sites=n)
