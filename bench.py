@@ -520,8 +520,8 @@ def run_ours(args, rank, world, local_rank):
         pool.close()
         cpu = {"value": cpu_sample.n_sites * passes / dt, "unit": UNIT, "cores": cores, "kind": pool.kind,
                "sample": "first %d sites of the workload, %d passes over %d worker processes (contiguous site "
-                         "batches), %.1f s wall; only the reference's tally_variant_read_fragments + "
-                         "bayesian_genotype are timed" % (cpu_sample.n_sites, passes, cores, dt)}
+                         "batches), %.1f s inside the reference's tally_variant_read_fragments + "
+                         "bayesian_genotype (slowest worker of each pass; nothing else is timed)" % (cpu_sample.n_sites, passes, cores, dt)}
 
     import torch
     import torch.distributed as dist
