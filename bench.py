@@ -522,6 +522,17 @@ def run_ours(args, rank, world, local_rank):
                "sample": "first %d sites of the workload, %d passes over %d worker processes (contiguous site "
                          "batches), %.1f s inside the reference's tally_variant_read_fragments + "
                          "bayesian_genotype (slowest worker of each pass; nothing else is timed)" % (cpu_sample.n_sites, passes, cores, dt)}
+        # the same functions on ONE core ("also report single-core"): the first 512 sites, ~3 s
+        one = cpu_sample.slice_sites(0, min(512, cpu_sample.n_sites))
+        pool1 = cpu_baseline.ReferencePool(one, 1)
+        pool1.step()
+        p1, d1 = 0, 0.0
+        while d1 < 3.0 and p1 < 50:
+            d1 += pool1.step()[0]
+            p1 += 1
+        pool1.close()
+        cpu["single_core"] = {"value": one.n_sites * p1 / d1, "unit": UNIT, "cores": 1, "kind": pool1.kind,
+                              "sample": "first %d sites, %d passes, %.1f s" % (one.n_sites, p1, d1)}
 
     import torch
     import torch.distributed as dist
