@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(kRWarps * 32) svgt_replay_pieces_kernel(const 
                 const bool sp = t >= cf;
                 const int left = sp ? ns - (t - cf) * 32 : nf - t * 32;
                 const int cnt = left > 32 ? 32 : left;
-                const int lead = s_lead[warp][b][i];
+                const int lead = max(s_lead[warp][b][i], 0);   /* scratch of a piece a malformed plan never scored holds anything */
                 if (!sp) c_replay_frag<ASSOC, 255>(&s_buf[warp][b][i][c][0], &s_buf[warp][b][i][0][0], c, cnt, lead, s_pm, acc, pend);
                 else if (c < 2) c_replay_split<ASSOC>(&s_buf[warp][b][i][c + 1][0], cnt, lead, acc, pend);
                 if (t == cf - 1) {                          /* the fragment rows are done */
