@@ -404,6 +404,7 @@ def test_bad_piece_plan_is_flagged(eng):
             dev.tensors["plan_pieces"][0, 3] = dev.plan.scratch_chunks
         else:
             dev.tensors["plan_heavy"][0, 2] += 1
+        dev.tensors["plan_scratch"].fill_(255)      # whatever an unscored piece leaves behind: lead counts of -1, NaN addends
         torch.cuda.synchronize()
         eng.score(dev)
         with pytest.raises(native.SvgtError) as ei:
