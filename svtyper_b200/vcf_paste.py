@@ -34,61 +34,55 @@ def open_vcf(path):
     return gzip.open(path, "rt") if path.endswith(".gz") else open(path, "r")
 
 
+def _header(handle, echo=None):
+    """The fields of the column-header line.  Master (`echo` given): its `##` lines are echoed and the first other
+    line is taken, whatever it is (:57-66).  Inputs: everything up to the first line that starts with a single `#` is
+    skipped, `[]` at end of file (:68-78)."""
+    for text in handle:
+        if text.startswith("##"):
+            if echo is not None:
+                echo.write(text.rstrip() + "\n")
+        elif echo is not None or text.startswith("#"):
+            return text.rstrip().split("\t", MAX_SPLIT)
+    return []
+
+
 def svt_join(master, sum_quals, vcf_list, out=None):
     """master: open text file or None (then the first VCF's path is re-opened); vcf_list: open text files."""
     out = sys.stdout if out is None else out
-    if master is None:
-        master = open_vcf(vcf_list[0].name)
+    master = open_vcf(vcf_list[0].name) if master is None else master
+    inputs = list(vcf_list)
     try:
-        master_line = ""
-        while True:                                         # header
-            master_line = master.readline()
-            if not master_line or master_line[:2] != "##":
-                break
-            out.write(master_line.rstrip() + "\n")
-        out_v = master_line.rstrip().split("\t", MAX_SPLIT)[:9]
-        for vcf in vcf_list:                                # sample names
-            while True:
-                line = vcf.readline()
-                if not line:
-                    break
-                if line[:2] == "##":
-                    continue
-                if line[0] == "#":
-                    out_v = out_v + line.rstrip().split("\t", MAX_SPLIT)[9:]
-                    break
-        out.write("\t".join(out_v) + "\n")
-        lines = []
-        while True:                                         # body
-            master_line = master.readline()
-            if not master_line:
-                break
-            out_v = master_line.rstrip().split("\t", MAX_SPLIT)[:8]
-            qual = float(out_v[5])
-            fmt = None
-            for vcf in vcf_list:
-                line = vcf.readline()
-                if not line:
-                    out.write("".join(lines))
+        names = _header(master, echo=out)[:9]               # the master keeps only its first nine columns
+        for handle in inputs:
+            names += _header(handle)[9:]
+        out.write("\t".join(names) + "\n")
+        pending = []
+        for record in master:
+            fixed = record.rstrip().split("\t", MAX_SPLIT)[:8]
+            total = float(fixed[5])                          # the master's own QUAL is part of the sum
+            samples, fmt = [], None
+            for handle in inputs:
+                text = handle.readline()
+                if not text:
+                    out.write("".join(pending))
                     sys.stderr.write("\nError: VCF files differ in length\n")
                     sys.exit(1)
-                line_v = line.rstrip().split("\t", MAX_SPLIT)
-                if fmt is None:
-                    fmt = line_v[8]
-                    out_v.append(fmt)
-                qual += float(line_v[5])
-                out_v = out_v + line_v[9:]
+                cols = text.rstrip().split("\t", MAX_SPLIT)
+                fmt = cols[8] if fmt is None else fmt        # FORMAT of the first input, not of the master
+                total += float(cols[5])
+                samples += cols[9:]
             if sum_quals:
-                out_v[5] = py2_float_str(qual)
-            lines.append("\t".join(out_v) + "\n")
-            if len(lines) >= 4096:
-                out.write("".join(lines))
-                lines = []
-        out.write("".join(lines))
+                fixed[5] = py2_float_str(total)
+            pending.append("\t".join(fixed + ([fmt] if fmt is not None else []) + samples) + "\n")
+            if len(pending) >= 4096:
+                out.write("".join(pending))
+                pending = []
+        out.write("".join(pending))
     finally:
         master.close()
-        for vcf in vcf_list:
-            vcf.close()
+        for handle in inputs:
+            handle.close()
 
 
 def get_args(argv=None):
